@@ -1,0 +1,142 @@
+/*
+ * yolo_head.h -- C ABI of libyolohead.so, the B200 (sm_100a) implementation of the YOLOv4 detection-head hot
+ * path of zjykzj/YOLOv4.  The reference is pure Python and has no FFI of its own: the
+ * reference-side boundary is the Python call surface of three symbols, and this header is what the Python
+ * shim (yolov4_b200/_cabi.py, ctypes) binds to replace each of them.  Every entry point cites the
+ * reference interface it replaces.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only; no torch / C++ types.
+ *   - every function returns int: 0 = YL_OK, 1..99 = argument errors, 1000+e = cudaError_t e.  Never throws.
+ *   - all device-pointer functions are stream-ordered on `stream` (a cudaStream_t passed as void*), do not
+ *     allocate, do not synchronise, and are CUDA-graph capturable.
+ *   - fp32 everywhere (the reference trains and evaluates with apex O0, README.md:106,112).
+ *   - sigmoid / exp / log are the "spec math" of DESIGN.md section 4 (fixed IEEE op sequences), so results are
+ *     bit-reproducible and identical to the CPU oracle.
+ */
+#ifndef YOLO_HEAD_H_
+#define YOLO_HEAD_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define YL_OK 0
+#define YL_ERR_ARG 1          /* null pointer / non-positive size / unsupported shape */
+#define YL_ERR_CLASSES 2      /* more classes than the candidate bitmask supports (YL_MAX_CLASSES) */
+#define YL_ERR_WORKSPACE 3    /* workspace smaller than yl_post_workspace_bytes() */
+#define YL_ERR_CAPACITY 4     /* yl_detect_host: a class segment overflowed cap_seg; recreate the context larger */
+#define YL_ERR_CUDA_BASE 1000 /* 1000 + cudaError_t */
+
+#define YL_MAX_CLASSES 128
+#define YL_ABI_VERSION 1
+
+typedef void *yl_stream_t; /* cudaStream_t */
+
+int yl_abi_version(void);
+const char *yl_error_string(int code);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * A2  YOLOLayer.forward, eval branch                       replaces yolo/model/yololayer.py:88-120,146-166
+ *   raw   [B, 3*(5+C), F, F] contiguous device fp32 (head conv output, yolov4.py:235-251)
+ *   anch_grid[6] = masked anchors / stride, (w0,h0,w1,h1,w2,h2)               (yololayer.py:73-76)
+ *   out   rows of (5+C) floats; box (b,a,y,x) -> row b*rows_per_image + row_offset + a*F*F + y*F + x, so the
+ *         three layers can write straight into the torch.cat((x1,x2,x3),1) buffer of yolov4.py:324.
+ * The reference's in-place overwrite of `raw` (a side effect nobody reads) is not reproduced.
+ * --------------------------------------------------------------------------------------------------------- */
+int yl_decode_dense(const float *raw, int B, int F, int C, const float *anch_grid, float stride,
+                    float *out, long rows_per_image, long row_offset, yl_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * A3  YOLOLayer.forward, train branch                      replaces yolo/model/yololayer.py:122-145
+ *   output_planar [B,3,5+C,F,F]: sigmoid on xy/obj/cls, raw wh.  The reference's dict['output'] is the
+ *                 permute(0,1,3,4,2) view of this storage (strides (255F^2, 85F^2, F, 1, F^2)).
+ *   pred_planar   [B,3,4,F,F]: grid-unit boxes (no *stride); dict['pred'] is its permuted view.
+ * yl_decode_train_backward: grad_raw = grad_out * d(output)/d(raw) (sigmoid' on xy/obj/cls, 1 on wh), for
+ * the autograd.Function that keeps `output` differentiable (yololoss.py:402-432 back-props through it).
+ * --------------------------------------------------------------------------------------------------------- */
+int yl_decode_train(const float *raw, int B, int F, int C, const float *anch_grid,
+                    float *output_planar, float *pred_planar, yl_stream_t stream);
+int yl_decode_train_backward(const float *output_planar, const float *grad_out_planar, int B, int F, int C,
+                             float *grad_raw, yl_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * A4+A5  postprocess(prediction, num_classes, conf_thre, nms_thre)   replaces yolo/util/utils.py:92-223
+ *        (and nms, utils.py:32-89, which it calls per (image, class))
+ *
+ * Two front ends fill the same candidate workspace, one back end consumes it:
+ *   yl_filter_raw     fused decode + confidence filter straight from the three raw head tensors (the 495 MB
+ *                     dense [B,M,5+C] tensor is never materialised)          yololayer.py:88-166 + utils.py:117-184
+ *   yl_filter_dense   confidence filter of an already decoded [B,M,5+C] tensor -- the literal
+ *                     postprocess(prediction, ...) entry                      utils.py:117-184
+ *   yl_nms            per (image,class) sort (score desc, box index desc) + greedy NMS (drop at IoU >= thr)
+ *                     + class-ascending concatenation                        utils.py:32-89, :191-220
+ *
+ * Workspace: one device buffer of yl_post_workspace_bytes(B, M, C, cap_seg) bytes.  cap_seg = capacity of one
+ * (image,class) candidate segment.  Counting is always exact; a segment that receives more than cap_seg
+ * candidates is reported through meta[] and the caller re-runs with a larger cap_seg (the shim does).
+ *
+ * Output: out_rows [B, cap_out, 7] = (x1,y1,x2,y2,obj_conf,cls_conf,cls_idx), image b's K_b rows first;
+ *         meta [3*B] int32: meta[b] = K_b (true count, may exceed cap_out -> rows truncated),
+ *                            meta[B+b] = max candidates seen in any class segment of image b,
+ *                            meta[2B+b] = total candidates of image b.
+ * --------------------------------------------------------------------------------------------------------- */
+size_t yl_post_workspace_bytes(int B, long M, int C, int cap_seg);
+
+/* Zeroes the per-run counters.  Must precede yl_filter_* on the same stream. */
+int yl_post_reset(void *ws, size_t ws_bytes, int B, long M, int C, int cap_seg, yl_stream_t stream);
+
+/* raw[l] = [B, 3*(5+C), F[l], F[l]], l = 0..n_layers-1 (n_layers <= 3), strides 8/16/32 (yololayer.py:54);
+ * anchors_px[18] and anchor_mask[9] are cfg MODEL.ANCHORS / ANCHOR_MASK.  M must equal sum 3*F[l]^2.
+ * img_first/img_count select a contiguous image range (used to pipeline image groups on several streams). */
+int yl_filter_raw(const float *const *raw, const int *F, int n_layers, int B, int C,
+                  const float *anchors_px, const int *anchor_mask, float conf_thre,
+                  void *ws, size_t ws_bytes, long M, int cap_seg, int img_first, int img_count,
+                  yl_stream_t stream);
+
+/* pred [B, M, 5+C] decoded (cx,cy,w,h,obj,cls...), not modified (the reference's in-place xyxy overwrite,
+ * utils.py:126, is an unobserved side effect).  num_classes <= C limits the row pre-filter (utils.py:139). */
+int yl_filter_dense(const float *pred, int B, long M, int C, int num_classes, float conf_thre,
+                    void *ws, size_t ws_bytes, int cap_seg, int img_first, int img_count, yl_stream_t stream);
+
+int yl_nms(void *ws, size_t ws_bytes, int B, long M, int C, int cap_seg, float nms_thre,
+           float *out_rows, long cap_out, int *meta, int img_first, int img_count, yl_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * A6+A7  YOLOLoss.build_target(output, pred, layer_no, labels)      replaces yolo/model/yololoss.py:118-371
+ *        (and bboxes_iou, yololoss.py:16-91, which it calls twice per image)
+ *   pred          element (b,a,j,i,k) at pred[b*ps[0] + a*ps[1] + j*ps[2] + i*ps[3] + k*ps[4]] (floats); the
+ *                 reference passes a non-contiguous view with strides (255F^2, 85F^2, F, 1, F^2)
+ *   labels        [B,K,5] fp32 (xc,yc,w,h,cls) in input pixels, zero padded (transform.py:464-471)
+ *   outputs       dense contiguous fp32: target [B,3,F,F,5+C], obj_mask [B,3,F,F], tgt_mask [B,3,F,F,4+C],
+ *                 tgt_scale [B,3,F,F,2]  (yololoss.py:156-167)
+ *   status        device int32[1], set non-zero if a matched GT indexes outside the grid (the reference
+ *                 raises IndexError there); may be NULL.
+ * --------------------------------------------------------------------------------------------------------- */
+int yl_build_target(const float *pred, const long *pred_strides, const float *labels, int B, int F, int K,
+                    int C, int layer_no, const float *anchors_px, const int *anchor_mask3, float ignore_thre,
+                    float *target, float *obj_mask, float *tgt_mask, float *tgt_scale, int *status,
+                    yl_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Host-buffer entry (what a non-Python caller binds; also the bench's end-to-end leg): raw head tensors in
+ * HOST memory -> detections in HOST memory.  The context owns device staging buffers, workspace, streams and
+ * pinned bounce buffers; H2D copies, kernels and the D2H of rows/counts are all inside the call.
+ *   raw_host[l] [B, 3*(5+C), F[l], F[l]] fp32 host (pinned or pageable)
+ *   out_rows_host [B, cap_out, 7], counts_host [B]
+ * Returns YL_OK; counts_host[b] > cap_out means image b was truncated.
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct yl_context yl_context;
+int yl_context_create(yl_context **ctx, int device, int B, const int *F, int n_layers, int C,
+                      const float *anchors_px, const int *anchor_mask, int cap_seg, long cap_out);
+int yl_context_destroy(yl_context *ctx);
+int yl_detect_host(yl_context *ctx, const float *const *raw_host, float conf_thre, float nms_thre,
+                   float *out_rows_host, int *counts_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YOLO_HEAD_H_ */

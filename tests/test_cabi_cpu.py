@@ -1,0 +1,72 @@
+"""CPU-only checks of the drop-in boundary: the C-ABI library builds, loads and exports every symbol that
+include/yolo_head.h declares; host-side argument validation needs no GPU."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "yolo_head.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(yl_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_builds_loads_and_exports_header_symbols():
+    from yolov4_b200 import _cabi, build
+    path = build.build_lib()
+    assert os.path.exists(path)
+    L = ctypes.CDLL(path)
+    declared = _declared_symbols()
+    assert len(declared) >= 14
+    for name in declared:
+        assert hasattr(L, name), "libyolohead.so does not export %s" % name
+    assert sorted(_cabi.EXPORTS) == declared
+    assert _cabi.lib().yl_abi_version() == 1
+
+
+def test_pure_host_entry_points_without_gpu():
+    from yolov4_b200 import _cabi
+    L = _cabi.lib()
+    # workspace sizing is host arithmetic
+    n = L.yl_post_workspace_bytes(64, 22743, 80, 1024)
+    assert n > 64 * 80 * 1024 * 16
+    assert L.yl_post_workspace_bytes(64, 22743, 80, 4096) > n
+    assert L.yl_post_workspace_bytes(0, 1, 1, 1) == 0
+    assert L.yl_error_string(0) == b"ok"
+    assert b"cap_seg" in L.yl_error_string(4)
+    # argument validation happens before any CUDA call
+    assert L.yl_filter_dense(None, 1, 10, 80, 80, 0.5, None, 0, 16, 0, 1, None) == 1
+    assert L.yl_build_target(None, None, None, 1, 4, 60, 80, 0, None, None, 0.7, None, None, None, None, None, None) == 1
+
+
+def test_host_wrappers_reject_cpu_and_wrong_dtype():
+    import yolov4_b200 as yb
+    cfg = {"ANCHORS": yb.ANCHORS_PX, "ANCHOR_MASK": yb.ANCHOR_MASK, "N_CLASSES": 80}
+    layer = yb.YOLOLayer(cfg, 1)
+    assert layer.stride == 16 and layer.n_anchors == 3 and layer.masked_anchors.dtype == torch.float64
+    assert len(list(layer.state_dict().keys())) == 0            # checkpoints load unchanged (val.py:82-83)
+    with pytest.raises(TypeError):
+        layer.eval()(torch.zeros(1, 255, 4, 4))
+    with pytest.raises(ValueError):
+        layer.eval()(torch.zeros(1, 254, 4, 4))
+    with pytest.raises(TypeError):
+        yb.postprocess(torch.zeros(1, 10, 85, dtype=torch.float64), 80)
+    with pytest.raises(ValueError):
+        yb.postprocess(torch.zeros(10, 85), 80)
+    with pytest.raises(TypeError):
+        yb.detect_raw([torch.zeros(1, 255, 4, 4)], 80)
+
+
+def test_synth_generator_is_seeded_and_shaped():
+    from yolov4_b200.synth import synth_head_outputs, synth_labels
+    a = synth_head_outputs(2, 96, 80, seed=3)
+    b = synth_head_outputs(2, 96, 80, seed=3)
+    assert [tuple(t.shape) for t in a] == [(2, 255, 12, 12), (2, 255, 6, 6), (2, 255, 3, 3)]
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+    lab = synth_labels(3, 608, n_valid=50)
+    assert lab.shape == (3, 60, 5) and (lab[:, 50:] == 0).all() and (lab[:, :50, 2:4] > 0).all()

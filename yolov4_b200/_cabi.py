@@ -1,0 +1,92 @@
+"""ctypes binding of libyolohead.so (include/yolo_head.h).  No torch types cross this boundary: tensors are
+passed as data_ptr() integers, the stream as torch.cuda.current_stream().cuda_stream.
+
+There is no CPU or PyTorch fallback: if the library is missing (and cannot be built) or a call fails, this raises.
+"""
+import ctypes
+import os
+
+from . import build as _build
+
+_f = ctypes.c_float
+_i = ctypes.c_int
+_l = ctypes.c_long
+_p = ctypes.c_void_p
+_sz = ctypes.c_size_t
+
+_lib = None
+
+
+class YoloHeadError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if not os.path.exists(path):
+        # build from source if a toolchain is present; otherwise fail loudly (never fall back to eager PyTorch)
+        path = _build.build_lib()
+    L = ctypes.CDLL(path)
+    L.yl_abi_version.restype = _i
+    L.yl_abi_version.argtypes = []
+    L.yl_error_string.restype = ctypes.c_char_p
+    L.yl_error_string.argtypes = [_i]
+    L.yl_decode_dense.restype = _i
+    L.yl_decode_dense.argtypes = [_p, _i, _i, _i, _p, _f, _p, _l, _l, _p]
+    L.yl_decode_train.restype = _i
+    L.yl_decode_train.argtypes = [_p, _i, _i, _i, _p, _p, _p, _p]
+    L.yl_decode_train_backward.restype = _i
+    L.yl_decode_train_backward.argtypes = [_p, _p, _i, _i, _i, _p, _p]
+    L.yl_post_workspace_bytes.restype = _sz
+    L.yl_post_workspace_bytes.argtypes = [_i, _l, _i, _i]
+    L.yl_post_reset.restype = _i
+    L.yl_post_reset.argtypes = [_p, _sz, _i, _l, _i, _i, _p]
+    L.yl_filter_raw.restype = _i
+    L.yl_filter_raw.argtypes = [_p, _p, _i, _i, _i, _p, _p, _f, _p, _sz, _l, _i, _i, _i, _p]
+    L.yl_filter_dense.restype = _i
+    L.yl_filter_dense.argtypes = [_p, _i, _l, _i, _i, _f, _p, _sz, _i, _i, _i, _p]
+    L.yl_nms.restype = _i
+    L.yl_nms.argtypes = [_p, _sz, _i, _l, _i, _i, _f, _p, _l, _p, _i, _i, _p]
+    L.yl_build_target.restype = _i
+    L.yl_build_target.argtypes = [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _f, _p, _p, _p, _p, _p, _p]
+    L.yl_context_create.restype = _i
+    L.yl_context_create.argtypes = [ctypes.POINTER(_p), _i, _i, _p, _i, _i, _p, _p, _i, _l]
+    L.yl_context_destroy.restype = _i
+    L.yl_context_destroy.argtypes = [_p]
+    L.yl_detect_host.restype = _i
+    L.yl_detect_host.argtypes = [_p, _p, _f, _f, _p, _p]
+    if L.yl_abi_version() != 1:
+        raise YoloHeadError("libyolohead.so ABI version mismatch")
+    _lib = L
+    return L
+
+
+EXPORTS = [
+    "yl_abi_version", "yl_error_string", "yl_decode_dense", "yl_decode_train", "yl_decode_train_backward",
+    "yl_post_workspace_bytes", "yl_post_reset", "yl_filter_raw", "yl_filter_dense", "yl_nms", "yl_build_target",
+    "yl_context_create", "yl_context_destroy", "yl_detect_host",
+]
+
+
+def check(rc):
+    if rc != 0:
+        raise YoloHeadError("libyolohead: %s (code %d)" % (lib().yl_error_string(rc).decode(), rc))
+
+
+def floats(vals):
+    return (ctypes.c_float * len(vals))(*[float(v) for v in vals])
+
+
+def ints(vals):
+    return (ctypes.c_int * len(vals))(*[int(v) for v in vals])
+
+
+def longs(vals):
+    return (ctypes.c_long * len(vals))(*[int(v) for v in vals])
+
+
+def ptrs(vals):
+    return (ctypes.c_void_p * len(vals))(*[int(v) for v in vals])

@@ -1,0 +1,95 @@
+"""YOLOLoss -- drop-in for yolo/model/yololoss.py: build_target runs in libyolohead.so (yl_build_target).
+
+build_target(output, pred, layer_no, labels) -> (target, obj_mask, tgt_mask, tgt_scale)      (yololoss.py:118-371)
+forward(outputs, targets) restates the reference's loss arithmetic (yololoss.py:373-443) in plain torch so the
+class can replace the reference's criterion as a whole; that arithmetic is SURVEY.md's "next" row N2, not part of
+the accelerated path.
+"""
+import numpy as np
+import torch
+from torch import nn
+
+from . import _cabi
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def build_target(output, pred, layer_no, labels, anchors, anchor_mask, ignore_thresh, n_classes, strict=False):
+    """Functional form.  output: only shape/dtype/device are used (as in the reference); pred [B,3,F,F,4] any strides;
+    labels [B,K,5] (xc,yc,w,h,cls) in input pixels, zero padded, any float dtype (cast to fp32 like yololoss.py:129).
+    strict=True synchronises and raises IndexError when a matched GT falls outside the grid, as the reference does."""
+    if not pred.is_cuda or pred.dtype != torch.float32:
+        raise TypeError("build_target (B200) needs float32 CUDA tensors; there is no CPU fallback")
+    B, A, F = int(output.shape[0]), int(output.shape[1]), int(output.shape[2])
+    n_ch = 5 + n_classes
+    assert output.shape[-1] == n_ch and A == 3
+    dev = pred.device
+    lab = labels.to(device=dev, dtype=torch.float32).contiguous()
+    K = int(lab.shape[1])
+    target = torch.empty((B, 3, F, F, n_ch), dtype=torch.float32, device=dev)
+    obj_mask = torch.empty((B, 3, F, F), dtype=torch.float32, device=dev)
+    tgt_mask = torch.empty((B, 3, F, F, 4 + n_classes), dtype=torch.float32, device=dev)
+    tgt_scale = torch.empty((B, 3, F, F, 2), dtype=torch.float32, device=dev)
+    status = torch.empty((1,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _cabi.check(_cabi.lib().yl_build_target(
+            pred.data_ptr(), _cabi.longs(pred.stride()), lab.data_ptr(), B, F, K, n_classes, int(layer_no),
+            _cabi.floats([v for wh in anchors for v in wh]), _cabi.ints(anchor_mask[layer_no]),
+            float(np.float32(ignore_thresh)), target.data_ptr(), obj_mask.data_ptr(), tgt_mask.data_ptr(),
+            tgt_scale.data_ptr(), status.data_ptr(), _stream()))
+    if strict and int(status.item()) != 0:
+        raise IndexError("a matched ground-truth box indexes outside the %dx%d grid" % (F, F))
+    return target, obj_mask, tgt_mask, tgt_scale
+
+
+class YOLOLoss(nn.Module):
+    strides = [8, 16, 32]
+
+    def __init__(self, cfg, ignore_thresh=0.7, device=None):
+        super().__init__()
+        self.cfg = cfg
+        self.ignore_thresh = ignore_thresh
+        self.device = device
+        self.anchors = cfg['ANCHORS']
+        self.n_classes = cfg['N_CLASSES']
+        self.l2_loss = nn.MSELoss(reduction="sum").to(device)
+        self.bce_loss = nn.BCELoss(reduction="sum").to(device)
+
+    def build_target(self, output, pred, layer_no, labels):
+        # side-effect attributes of the reference (yololoss.py:133-150); nothing reads them afterwards
+        self.anch_mask = self.cfg['ANCHOR_MASK'][layer_no]
+        self.n_anchors = len(self.anch_mask)
+        self.stride = self.strides[layer_no]
+        self.all_anchors_grid = [(w / self.stride, h / self.stride) for w, h in self.anchors]
+        self.masked_anchors = [self.all_anchors_grid[i] for i in self.anch_mask]
+        return build_target(output, pred, layer_no, labels, self.anchors, self.cfg['ANCHOR_MASK'], self.ignore_thresh,
+                            self.n_classes)
+
+    def forward(self, outputs, targets):
+        assert isinstance(outputs, list) and isinstance(targets, dict)
+        total = 0
+        for od in outputs:
+            layer_no = od['layer_no']
+            output = od['output'].to(self.device)
+            pred = od['pred'].to(self.device)
+            labels = targets['padded_labels'].to(self.device)
+            target, obj_mask, tgt_mask, tgt_scale = self.build_target(output, pred, layer_no, labels)
+            n_ch = output.shape[-1]
+            sel = np.r_[0:4, 5:n_ch]
+            # yololoss.py:402-414 (written out of place; same values)
+            out_m = output.clone()
+            out_m[..., 4] = output[..., 4] * obj_mask
+            out_m[..., sel] = output[..., sel] * tgt_mask
+            out_m[..., 2:4] = out_m[..., 2:4] * tgt_scale
+            target[..., 4] *= obj_mask
+            target[..., sel] *= tgt_mask
+            target[..., 2:4] *= tgt_scale
+            bce_w = nn.BCELoss(weight=tgt_scale * tgt_scale, reduction="sum")
+            loss_xy = bce_w(out_m[..., :2], target[..., :2])
+            loss_wh = self.l2_loss(out_m[..., 2:4], target[..., 2:4]) / 2
+            loss_obj = self.bce_loss(out_m[..., 4], target[..., 4])
+            loss_cls = self.bce_loss(out_m[..., 5:], target[..., 5:])
+            total = total + loss_xy + loss_wh + loss_obj + loss_cls
+        return total
