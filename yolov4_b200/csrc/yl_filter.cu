@@ -27,71 +27,217 @@ __device__ __forceinline__ float class_logit_bound(float obj, float thr)
     return L - 0.01f - 1e-3f * fabsf(L);
 }
 
-template <int VEC, int NW>
-__global__ void __launch_bounds__(K1_THREADS)
-k_filter_raw(const float *__restrict__ raw, int Fw, int F2, int C, float stride,
-             float aw0, float ah0, float aw1, float ah1, float aw2, float ah2,
-             int row_off, long M, float thr, int cap_seg, int img_first,
-             uint4 *__restrict__ cand, unsigned *__restrict__ seg_count,
-             float4 *__restrict__ boxtab, float *__restrict__ objtab)
+// One scale of the head as the kernel sees it.
+struct RawLayer {
+    const float *raw;      // [B, 3, 5+C, F, F]
+    int Fw, F2;
+    int row_off;           // rows of the lower scales in the concatenated [M] axis (yolov4.py:324)
+    int tiles;             // CTAs along x for this scale
+    int vec;               // 4 = 128-bit loads, 1 = scalar loads (planes not 16-byte aligned, e.g. 19x19)
+    float stride;
+    float aw[3], ah[3];    // masked anchors in grid units (yololayer.py:73-76)
+};
+struct RawParams {
+    RawLayer layer[3];
+    int n_layers, C, cap_seg, img_first;
+    long M;
+    float thr;
+    uint4 *cand;
+    unsigned *seg_count;
+    float4 *boxtab;
+    float *objtab;
+};
+
+constexpr int K1_WARPS = K1_THREADS / 32;
+constexpr int K1_QCAP = 512;           // flagged (box,class) pairs a warp resolves cooperatively per tile
+
+struct K1Smem {
+    unsigned short ent[K1_WARPS][K1_QCAP];   // bit15 pass | box slot (7b) << 8 | class (7b)
+    unsigned cls[K1_WARPS][K1_QCAP];         // sigmoid(class logit) bits of passing entries
+    float obj[K1_WARPS][128];
+    unsigned any[K1_WARPS][4], nan[K1_WARPS][4];
+};
+
+// Decode one box (yololayer.py:150-162) and convert to corners (utils.py:117-126).
+__device__ __forceinline__ float4 decode_box(const float *bp, int F2, int Fw, int p, float aw, float ah, float stride)
 {
-    const int p0 = (blockIdx.x * K1_THREADS + threadIdx.x) * VEC;
-    if (p0 >= F2) return;
-    const int ba = img_first * 3 + blockIdx.y;
+    const float tx = bp[0], ty = bp[(size_t)F2], tw = bp[2 * (size_t)F2], th = bp[3 * (size_t)F2];
+    const int gy = p / Fw, gx = p - gy * Fw;
+    const float bx = __fmul_rn(__fadd_rn(spec_sigmoidf(tx), (float)gx), stride);
+    const float by = __fmul_rn(__fadd_rn(spec_sigmoidf(ty), (float)gy), stride);
+    const float bw = __fmul_rn(__fmul_rn(spec_expf(tw), aw), stride);
+    const float bh = __fmul_rn(__fmul_rn(spec_expf(th), ah), stride);
+    const float hw = __fmul_rn(bw, 0.5f), hh = __fmul_rn(bh, 0.5f);
+    return make_float4(__fsub_rn(bx, hw), __fsub_rn(by, hh), __fadd_rn(bx, hw), __fadd_rn(by, hh));
+}
+
+// One tile = K1_THREADS*VEC consecutive boxes of one (image, anchor).  Phase 1 streams the class planes with one
+// compare per logit; phase 2 resolves the ~1% flagged pairs warp-cooperatively (all lanes, all loads in flight
+// together) instead of serially in the lane that owns the box.
+template <int VEC, int NW>
+__device__ __forceinline__ void filter_tile(const RawParams &P, const RawLayer &Ly, int tile, int ba, K1Smem &sm)
+{
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int C = P.C, F2 = Ly.F2;
+    const float thr = P.thr;
+    const int p0 = (tile * K1_THREADS + threadIdx.x) * VEC;
+    const bool inb = p0 < F2;                                        // F2 % VEC == 0, so a vector is all in or all out
     const int b = ba / 3, a = ba - 3 * b;
     const int nch = 5 + C;
-    const float *base = raw + ((size_t)ba * nch) * F2 + p0;
+    const float *base = Ly.raw + ((size_t)ba * nch) * F2 + (inb ? p0 : 0);
+    const float *cp = base + 5 * (size_t)F2;
 
-    Vec<VEC> tob;
-    tob.load(base + 4 * (size_t)F2);
     float obj[VEC], lth[VEC];
     bool any_alive = false;
+    if (inb) {
+        Vec<VEC> tob;
+        tob.load(base + 4 * (size_t)F2);
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) {
-        obj[v] = spec_sigmoidf(tob.v[v]);
-        lth[v] = class_logit_bound(obj[v], thr);
-        any_alive |= (lth[v] != kInf);
+        for (int v = 0; v < VEC; ++v) {
+            obj[v] = spec_sigmoidf(tob.v[v]);
+            lth[v] = class_logit_bound(obj[v], thr);
+            any_alive |= (lth[v] != kInf);
+        }
+    } else {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) { obj[v] = 0.0f; lth[v] = kInf; }
     }
-    if (!any_alive) return;
 
-    // ---- streaming pass: one compare per class logit, result bits kept in registers -----------------------
+    // ---- phase 1: streaming pass, result bits kept in registers -------------------------------------------------
     unsigned bits[VEC][NW];
 #pragma unroll
     for (int v = 0; v < VEC; ++v)
 #pragma unroll
         for (int w = 0; w < NW; ++w) bits[v][w] = 0u;
-
-    const float *cp = base + 5 * (size_t)F2;
+    if (any_alive) {
 #pragma unroll
-    for (int w = 0; w < NW; ++w) {
-        const int kn = min(32, C - 32 * w);
+        for (int w = 0; w < NW; ++w) {
+            const int kn = min(32, C - 32 * w);
 #pragma unroll 1
-        for (int kk = 0; kk < kn; kk += 8) {
-            Vec<VEC> t[8];
+            for (int kk = 0; kk < kn; kk += 8) {
+                Vec<VEC> t[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u)
-                if (kk + u < kn) t[u].load(cp + (size_t)(32 * w + kk + u) * F2);
+                for (int u = 0; u < 8; ++u)
+                    if (kk + u < kn) t[u].load(cp + (size_t)(32 * w + kk + u) * F2);
 #pragma unroll
-            for (int u = 0; u < 8; ++u)
-                if (kk + u < kn) {
+                for (int u = 0; u < 8; ++u)
+                    if (kk + u < kn) {
 #pragma unroll
-                    for (int v = 0; v < VEC; ++v)
-                        bits[v][w] |= (t[u].v[v] < lth[v]) ? 0u : (1u << (kk + u));   // NaN logits set the bit too
-                }
+                        for (int v = 0; v < VEC; ++v)
+                            bits[v][w] |= (t[u].v[v] < lth[v]) ? 0u : (1u << (kk + u));   // NaN logits set the bit too
+                    }
+            }
         }
     }
-
-    // ---- exact pass over the flagged pairs (rare) ----------------------------------------------------------
-    const float aw = (a == 0) ? aw0 : ((a == 1) ? aw1 : aw2);
-    const float ah = (a == 0) ? ah0 : ((a == 1) ? ah1 : ah2);
+    int cnt = 0;
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
-        if (lth[v] == kInf) continue;
+        if (lth[v] == kInf) {
+#pragma unroll
+            for (int w = 0; w < NW; ++w) bits[v][w] = 0u;
+        }
+#pragma unroll
+        for (int w = 0; w < NW; ++w) cnt += __popc(bits[v][w]);
+    }
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += n;
+    }
+    const int total = __shfl_sync(FULL, incl, 31);
+    if (total == 0) return;                                          // warp-uniform
+
+    const float aw = Ly.aw[a], ah = Ly.ah[a];
+    const int row_base = Ly.row_off + a * F2;                        // + p = row inside the image
+    if (total <= K1_QCAP) {
+        // ---- phase 2: cooperative exact pass ------------------------------------------------------------------
+        unsigned short *ent = sm.ent[warp];
+        unsigned *ecls = sm.cls[warp];
+        int e = incl - cnt;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            sm.obj[warp][lane * VEC + v] = obj[v];
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                unsigned m = bits[v][w];
+                while (m) {
+                    const int bit = __ffs(m) - 1;
+                    m &= m - 1;
+                    ent[e++] = (unsigned short)(((lane * VEC + v) << 8) | (32 * w + bit));
+                }
+            }
+        }
+        if (lane < 4) { sm.any[warp][lane] = 0u; sm.nan[warp][lane] = 0u; }
+        __syncwarp();
+        const int wp0 = __shfl_sync(FULL, p0, 0);                    // first box of the warp (lane 0 is in bounds when total > 0)
+        const float *wbase = Ly.raw + ((size_t)ba * nch) * F2 + wp0;
+        const float *wcp = wbase + 5 * (size_t)F2;
+        for (int e0 = 0; e0 < total; e0 += 128) {
+            float t[4];
+            unsigned en[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int q = e0 + 32 * u + lane;
+                en[u] = (q < total) ? ent[q] : 0xFFFFu;
+                t[u] = (q < total) ? wcp[(size_t)(en[u] & 0x7F) * F2 + (en[u] >> 8)] : 0.0f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int q = e0 + 32 * u + lane;
+                if (q < total) {
+                    const int bs = en[u] >> 8;
+                    // a NaN class logit makes torch.max (utils.py:139) NaN and drops the whole row (:145)
+                    if (t[u] != t[u]) atomicOr(&sm.nan[warp][bs >> 5], 1u << (bs & 31));
+                    const float cls = spec_sigmoidf(t[u]);
+                    if (__fmul_rn(sm.obj[warp][bs], cls) >= thr) {
+                        atomicOr(&sm.any[warp][bs >> 5], 1u << (bs & 31));
+                        ecls[q] = __float_as_uint(cls);
+                        ent[q] = (unsigned short)(en[u] | 0x8000u);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        // boxes with at least one surviving pair: decode once, store corners + objectness
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            const int bs = lane + 32 * j;
+            const unsigned live = (sm.any[warp][bs >> 5] & ~sm.nan[warp][bs >> 5]) >> (bs & 31) & 1u;
+            if (live) {
+                const int p = wp0 + bs;
+                const size_t brow = (size_t)b * P.M + (row_base + p);
+                P.boxtab[brow] = decode_box(wbase + bs, F2, Ly.Fw, p, aw, ah, Ly.stride);
+                P.objtab[brow] = sm.obj[warp][bs];
+            }
+        }
+        // one record per surviving (box,class) pair
+        for (int q = lane; q < total; q += 32) {
+            const unsigned en = ent[q];
+            const int bs = (en >> 8) & 0x7F;
+            if ((en & 0x8000u) && !((sm.nan[warp][bs >> 5] >> (bs & 31)) & 1u)) {
+                const int k = en & 0x7F;
+                const float cls = __uint_as_float(ecls[q]);
+                const float s = __fadd_rn(__fmul_rn(sm.obj[warp][bs], cls), 0.0f);      // +0 canonicalises -0
+                const unsigned seg = (unsigned)(b * C + k);
+                const unsigned slot = atomicAdd(&P.seg_count[seg], 1u);
+                if (slot < (unsigned)P.cap_seg)
+                    P.cand[(size_t)seg * P.cap_seg + slot] =
+                        make_uint4(__float_as_uint(s), (unsigned)(row_base + wp0 + bs), __float_as_uint(cls), 0u);
+            }
+        }
+        __syncwarp();
+        return;
+    }
+
+    // ---- dense fallback (more than K1_QCAP flagged pairs in the warp: degenerate inputs): per-lane serial pass ------
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
         unsigned any = 0u;
 #pragma unroll
         for (int w = 0; w < NW; ++w) any |= bits[v][w];
         if (!any) continue;
-        // A: exact test; a NaN class logit makes torch.max (utils.py:139) NaN and drops the whole row (:145)
         bool nan_row = false;
 #pragma unroll
         for (int w = 0; w < NW; ++w) {
@@ -101,8 +247,7 @@ k_filter_raw(const float *__restrict__ raw, int Fw, int F2, int C, float stride,
                 m &= m - 1;
                 const float t = cp[(size_t)(32 * w + bit) * F2 + v];
                 nan_row |= (t != t);
-                const float s = __fmul_rn(obj[v], spec_sigmoidf(t));
-                if (!(s >= thr)) bits[v][w] &= ~(1u << bit);
+                if (!(__fmul_rn(obj[v], spec_sigmoidf(t)) >= thr)) bits[v][w] &= ~(1u << bit);
             }
         }
         if (nan_row) continue;
@@ -110,19 +255,11 @@ k_filter_raw(const float *__restrict__ raw, int Fw, int F2, int C, float stride,
 #pragma unroll
         for (int w = 0; w < NW; ++w) any |= bits[v][w];
         if (!any) continue;
-        // B: decode the box once (yololayer.py:150-162) and convert to corners (utils.py:117-126)
         const int p = p0 + v;
-        const int gy = p / Fw, gx = p - gy * Fw;
-        const float bx = __fmul_rn(__fadd_rn(spec_sigmoidf(base[v]), (float)gx), stride);
-        const float by = __fmul_rn(__fadd_rn(spec_sigmoidf(base[(size_t)F2 + v]), (float)gy), stride);
-        const float bw = __fmul_rn(__fmul_rn(spec_expf(base[2 * (size_t)F2 + v]), aw), stride);
-        const float bh = __fmul_rn(__fmul_rn(spec_expf(base[3 * (size_t)F2 + v]), ah), stride);
-        const float hw = __fmul_rn(bw, 0.5f), hh = __fmul_rn(bh, 0.5f);
-        const unsigned row = (unsigned)(row_off + a * F2 + p);
-        const size_t brow = (size_t)b * M + row;
-        boxtab[brow] = make_float4(__fsub_rn(bx, hw), __fsub_rn(by, hh), __fadd_rn(bx, hw), __fadd_rn(by, hh));
-        objtab[brow] = obj[v];
-        // C: emit one record per surviving (box,class) pair
+        const unsigned row = (unsigned)(row_base + p);
+        const size_t brow = (size_t)b * P.M + row;
+        P.boxtab[brow] = decode_box(base + v, F2, Ly.Fw, p, aw, ah, Ly.stride);
+        P.objtab[brow] = obj[v];
 #pragma unroll
         for (int w = 0; w < NW; ++w) {
             unsigned m = bits[v][w];
@@ -131,14 +268,28 @@ k_filter_raw(const float *__restrict__ raw, int Fw, int F2, int C, float stride,
                 m &= m - 1;
                 const int k = 32 * w + bit;
                 const float cls = spec_sigmoidf(cp[(size_t)k * F2 + v]);
-                const float s = __fadd_rn(__fmul_rn(obj[v], cls), 0.0f);      // +0 canonicalises -0
+                const float s = __fadd_rn(__fmul_rn(obj[v], cls), 0.0f);
                 const unsigned seg = (unsigned)(b * C + k);
-                const unsigned slot = atomicAdd(&seg_count[seg], 1u);
-                if (slot < (unsigned)cap_seg)
-                    cand[(size_t)seg * cap_seg + slot] = make_uint4(__float_as_uint(s), row, __float_as_uint(cls), 0u);
+                const unsigned slot = atomicAdd(&P.seg_count[seg], 1u);
+                if (slot < (unsigned)P.cap_seg)
+                    P.cand[(size_t)seg * P.cap_seg + slot] = make_uint4(__float_as_uint(s), row, __float_as_uint(cls), 0u);
             }
         }
     }
+}
+
+// grid = (sum of tiles over the scales, img_count*3): one launch covers all scales of an image group.
+template <int NW>
+__global__ void __launch_bounds__(K1_THREADS)
+k_filter_raw(const __grid_constant__ RawParams P)
+{
+    __shared__ K1Smem sm;
+    const int ba = P.img_first * 3 + blockIdx.y;
+    int tile = blockIdx.x;
+    int l = 0;
+    while (l < P.n_layers - 1 && tile >= P.layer[l].tiles) { tile -= P.layer[l].tiles; ++l; }
+    if (P.layer[l].vec == 4) filter_tile<4, NW>(P, P.layer[l], tile, ba, sm);
+    else filter_tile<1, NW>(P, P.layer[l], tile, ba, sm);
 }
 
 // One warp per decoded row (5+C contiguous floats, <= 133): coalesced 128-byte reads, ballot-free emission.
@@ -209,29 +360,6 @@ k_filter_dense(const float *__restrict__ pred, long M, int C, int num_classes, f
     }
 }
 
-template <int VEC>
-static int launch_filter_raw(int NW, dim3 grid, cudaStream_t st, const float *raw, int Fw, int F2, int C, float stride,
-                             const float *ag, int row_off, long M, float thr, int cap_seg, int img_first,
-                             uint4 *cand, unsigned *seg_count, float4 *boxtab, float *objtab)
-{
-#define YL_K1_CASE(NW_)                                                                                           \
-    case NW_:                                                                                                     \
-        k_filter_raw<VEC, NW_><<<grid, K1_THREADS, 0, st>>>(raw, Fw, F2, C, stride, ag[0], ag[1], ag[2], ag[3],  \
-                                                            ag[4], ag[5], row_off, M, thr, cap_seg, img_first,  \
-                                                            cand, seg_count, boxtab, objtab);                  \
-        break;
-    switch (NW) {
-        YL_K1_CASE(1)
-        YL_K1_CASE(2)
-        YL_K1_CASE(3)
-        YL_K1_CASE(4)
-    default:
-        return YL_ERR_CLASSES;
-    }
-#undef YL_K1_CASE
-    return YL_OK;
-}
-
 }  // namespace yl
 
 using namespace yl;
@@ -271,33 +399,37 @@ extern "C" int yl_filter_raw(const float *const *raw, const int *F, int n_layers
     uint4 *cand = (uint4 *)(w + L.off_cand);
     float4 *boxtab = (float4 *)(w + L.off_box);
     float *objtab = (float *)(w + L.off_obj);
-    const int NW = (C + 31) / 32;
-    int row_off = 0;
-    for (int l = 0; l < n_layers; ++l) {
-        const int Fw = F[l], F2 = Fw * Fw;
-        const float stride = (float)(8 << l);                               // yololayer.py:54
-        float ag[6];
+    RawParams P;
+    P.n_layers = n_layers; P.C = C; P.cap_seg = cap_seg; P.img_first = img_first; P.M = M; P.thr = conf_thre;
+    P.cand = cand; P.seg_count = seg_count; P.boxtab = boxtab; P.objtab = objtab;
+    int row_off = 0, tiles_total = 0;
+    for (int l = 0; l < 3; ++l) {
+        RawLayer &Ly = P.layer[l];
+        if (l >= n_layers) { Ly = P.layer[0]; Ly.tiles = 0; continue; }
+        Ly.raw = raw[l]; Ly.Fw = F[l]; Ly.F2 = F[l] * F[l]; Ly.row_off = row_off;
+        Ly.stride = (float)(8 << l);                                        // yololayer.py:54
         for (int a = 0; a < 3; ++a) {                                       // yololayer.py:73-76 (doubles, then fp32)
             const int q = anchor_mask[3 * l + a];
-            ag[2 * a] = (float)((double)anchors_px[2 * q] / (double)stride);
-            ag[2 * a + 1] = (float)((double)anchors_px[2 * q + 1] / (double)stride);
+            if (q < 0 || q > 8) return YL_ERR_ARG;
+            Ly.aw[a] = (float)((double)anchors_px[2 * q] / (double)Ly.stride);
+            Ly.ah[a] = (float)((double)anchors_px[2 * q + 1] / (double)Ly.stride);
         }
         // 128-bit loads need 16-byte aligned planes: F^2 % 4 == 0 and an aligned base (19x19 / 13x13 grids fall back)
-        const bool vec4 = (F2 % 4 == 0) && (((uintptr_t)raw[l]) % 16 == 0);
-        int rc;
-        if (vec4) {
-            dim3 grid((F2 / 4 + K1_THREADS - 1) / K1_THREADS, img_count * 3);
-            rc = launch_filter_raw<4>(NW, grid, (cudaStream_t)stream, raw[l], Fw, F2, C, stride, ag, row_off, M, conf_thre,
-                                      cap_seg, img_first, cand, seg_count, boxtab, objtab);
-        } else {
-            dim3 grid((F2 + K1_THREADS - 1) / K1_THREADS, img_count * 3);
-            rc = launch_filter_raw<1>(NW, grid, (cudaStream_t)stream, raw[l], Fw, F2, C, stride, ag, row_off, M, conf_thre,
-                                      cap_seg, img_first, cand, seg_count, boxtab, objtab);
-        }
-        if (rc != YL_OK) return rc;
-        YL_LAUNCH_CHECK();
-        row_off += 3 * F2;
+        Ly.vec = ((Ly.F2 % 4 == 0) && (((uintptr_t)raw[l]) % 16 == 0)) ? 4 : 1;
+        Ly.tiles = (Ly.F2 / Ly.vec + K1_THREADS - 1) / K1_THREADS;
+        tiles_total += Ly.tiles;
+        row_off += 3 * Ly.F2;
     }
+    dim3 grid(tiles_total, img_count * 3);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch ((C + 31) / 32) {
+    case 1: k_filter_raw<1><<<grid, K1_THREADS, 0, st>>>(P); break;
+    case 2: k_filter_raw<2><<<grid, K1_THREADS, 0, st>>>(P); break;
+    case 3: k_filter_raw<3><<<grid, K1_THREADS, 0, st>>>(P); break;
+    case 4: k_filter_raw<4><<<grid, K1_THREADS, 0, st>>>(P); break;
+    default: return YL_ERR_CLASSES;
+    }
+    YL_LAUNCH_CHECK();
     return YL_OK;
 }
 

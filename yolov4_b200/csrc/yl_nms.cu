@@ -182,10 +182,142 @@ __device__ int greedy_nms(Store &s, int n, float thr, unsigned short *kept_s, un
     return *sh_nk;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Small tier (the common case: ~150 candidates per (image,class) at conf 1e-4): everything in ~18 KB of shared memory.
+//   1. rank sort on the unique 64-bit key (each thread counts the keys below its own; broadcast reads, no barriers)
+//   2. transposed suppression matrix T[j] = { i < j : IoU(i,j) >= thr }, one row per thread, all pairs independent
+//   3. warp 0 walks j in score order: kept[j] = (T[j] & kept) == 0        (utils.py:67-84)
+// Segments with more than SMALL_R candidates are queued for the big tier.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int SMALL_R = 256;
+constexpr int SMALL_W = SMALL_R / 32;
+constexpr int SMALL_THREADS = 128;
+
+template <bool POS>
+__device__ __forceinline__ void small_pairs(const float4 *sh_box, const float *sh_area, unsigned (*sh_T)[SMALL_W + 1], int n, float thr)
+{
+    for (int j = threadIdx.x; j < n; j += SMALL_THREADS) {
+        const float4 bj = sh_box[j];
+        const float aj = sh_area[j];
+#pragma unroll
+        for (int w = 0; w < SMALL_W; ++w) {
+            unsigned word = 0u;
+            const int lim = min(32, j - 32 * w);
+            for (int ii = 0; ii < lim; ++ii) {
+                const int i = 32 * w + ii;
+                const bool sup = POS ? suppresses_pos(bj, aj, sh_box[i], sh_area[i], thr) : suppresses_any(bj, aj, sh_box[i], sh_area[i], thr);
+                word |= sup ? (1u << ii) : 0u;
+            }
+            sh_T[j][w] = word;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(SMALL_THREADS)
+k_segment_nms_small(uint4 *__restrict__ cand, const unsigned *__restrict__ seg_count, unsigned *__restrict__ kept_count,
+                    const float4 *__restrict__ boxtab, long M, int C, int cap_seg, float thr, int seg_first,
+                    unsigned *__restrict__ big_count, unsigned *__restrict__ big_list)
+{
+    __shared__ unsigned long long sh_key[SMALL_R];
+    __shared__ unsigned sh_row[SMALL_R], sh_conf[SMALL_R];      // sorted
+    __shared__ float4 sh_box[SMALL_R];
+    __shared__ float sh_area[SMALL_R];
+    __shared__ unsigned sh_T[SMALL_R][SMALL_W + 1];             // +1: conflict-free row writes
+    __shared__ unsigned sh_kw[SMALL_W], sh_pref[SMALL_W + 1];
+
+    const int seg = seg_first + blockIdx.x;
+    const unsigned cnt = seg_count[seg];
+    if (cnt == 0u) return;                                      // kept_count was zeroed by yl_post_reset
+    if (cnt > (unsigned)cap_seg) return;                        // overflow: reported through meta[], caller re-runs
+    const int tid = threadIdx.x;
+    if (cnt > (unsigned)SMALL_R) {
+        if (tid == 0) big_list[atomicAdd(big_count, 1u)] = (unsigned)seg;
+        return;
+    }
+    const int n = (int)cnt;
+    const int b = seg / C;
+    uint4 *rec = cand + (size_t)seg * cap_seg;
+    const float4 *boxes = boxtab + (size_t)b * M;
+    const bool pos = thr > 0.0f;
+
+    // load (at most two records per thread), start the box gathers, then rank
+    unsigned long long key[2];
+    unsigned conf[2], row[2];
+    float4 bx[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int i = tid + u * SMALL_THREADS;
+        key[u] = ~0ull; conf[u] = 0u; row[u] = 0u;
+        if (i < n) {
+            const uint4 r = rec[i];
+            key[u] = ((unsigned long long)score_desc_bits(r.x) << 32) | (unsigned)(~r.y);
+            conf[u] = r.z; row[u] = r.y;
+            sh_key[i] = key[u];
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+        if (tid + u * SMALL_THREADS < n) bx[u] = boxes[row[u]];
+    __syncthreads();
+    int rank[2] = {0, 0};
+    for (int j = 0; j < n; ++j) {
+        const unsigned long long k = sh_key[j];
+        rank[0] += (k < key[0]) ? 1 : 0;
+        rank[1] += (k < key[1]) ? 1 : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+        if (tid + u * SMALL_THREADS < n) {
+            const int r = rank[u];
+            sh_row[r] = row[u]; sh_conf[r] = conf[u];
+            sh_area[r] = box_area(bx[u]);
+            sh_box[r] = pos ? sanitise(bx[u]) : bx[u];
+        }
+    __syncthreads();
+    if (pos) small_pairs<true>(sh_box, sh_area, sh_T, n, thr);
+    else small_pairs<false>(sh_box, sh_area, sh_T, n, thr);
+    __syncthreads();
+    if (tid < 32) {
+        unsigned keptw = 0u;                                    // lane w owns kept word w
+        const int lw = tid < SMALL_W ? tid : 0;
+        int j = 0;
+        for (; j + 4 <= n; j += 4) {
+            unsigned t0 = sh_T[j][lw], t1 = sh_T[j + 1][lw], t2 = sh_T[j + 2][lw], t3 = sh_T[j + 3][lw];
+            if (tid >= SMALL_W) { t0 = t1 = t2 = t3 = 0u; }
+            if (!__any_sync(0xFFFFFFFFu, t0 & keptw) && tid == (j >> 5)) keptw |= 1u << (j & 31);
+            if (!__any_sync(0xFFFFFFFFu, t1 & keptw) && tid == ((j + 1) >> 5)) keptw |= 1u << ((j + 1) & 31);
+            if (!__any_sync(0xFFFFFFFFu, t2 & keptw) && tid == ((j + 2) >> 5)) keptw |= 1u << ((j + 2) & 31);
+            if (!__any_sync(0xFFFFFFFFu, t3 & keptw) && tid == ((j + 3) >> 5)) keptw |= 1u << ((j + 3) & 31);
+        }
+        for (; j < n; ++j) {
+            const unsigned t0 = (tid < SMALL_W) ? sh_T[j][lw] : 0u;
+            if (!__any_sync(0xFFFFFFFFu, t0 & keptw) && tid == (j >> 5)) keptw |= 1u << (j & 31);
+        }
+        int c = (tid < SMALL_W) ? __popc(keptw) : 0, incl = c;
+#pragma unroll
+        for (int o = 1; o < SMALL_W; o <<= 1) {
+            const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (tid >= o) incl += v;
+        }
+        if (tid < SMALL_W) { sh_kw[tid] = keptw; sh_pref[tid] = (unsigned)(incl - c); }
+        if (tid == SMALL_W - 1) { sh_pref[SMALL_W] = (unsigned)incl; kept_count[seg] = (unsigned)incl; }
+    }
+    __syncthreads();
+    for (int j2 = tid; j2 < n; j2 += SMALL_THREADS) {
+        const unsigned kw = sh_kw[j2 >> 5];
+        if ((kw >> (j2 & 31)) & 1u) {
+            const unsigned q = sh_pref[j2 >> 5] + __popc(kw & ((1u << (j2 & 31)) - 1u));
+            rec[q] = make_uint4(sh_row[j2], sh_conf[j2], 0u, 0u);        // {box row, cls_conf bits}
+        }
+    }
+}
+
+// Big tier: persistent CTAs walk the list of segments the small tier could not take (more than SMALL_R candidates).
 __global__ void __launch_bounds__(NMS_THREADS)
-k_segment_nms(uint4 *__restrict__ cand, const unsigned *__restrict__ seg_count, unsigned *__restrict__ kept_count,
-              const float4 *__restrict__ boxtab, long M, int C, int cap_seg, float thr, int seg_first,
-              unsigned *__restrict__ kept_scratch /* [B*C*cap_seg] u32, only used by oversized segments; may be null */)
+k_segment_nms_big(uint4 *__restrict__ cand, const unsigned *__restrict__ seg_count, unsigned *__restrict__ kept_count,
+                  const float4 *__restrict__ boxtab, long M, int C, int cap_seg, float thr,
+                  const unsigned *__restrict__ big_count, const unsigned *__restrict__ big_list,
+                  unsigned *__restrict__ kept_scratch /* [B*C*cap_seg] u32, only when cap_seg > SMEM_R; else null */)
 {
     __shared__ unsigned long long sh_key[SMEM_R];
     __shared__ unsigned sh_conf[SMEM_R];
@@ -196,11 +328,11 @@ k_segment_nms(uint4 *__restrict__ cand, const unsigned *__restrict__ seg_count, 
     __shared__ unsigned sh_supp[2];
     __shared__ int sh_nk;
 
-    const int seg = seg_first + blockIdx.x;
+    const unsigned nbig = *big_count;
+    for (unsigned it = blockIdx.x; it < nbig; it += gridDim.x) {
+    const int seg = (int)big_list[it];
     const int b = seg / C;
     const unsigned cnt = seg_count[seg];
-    if (cnt == 0u) return;                                   // kept_count was zeroed by yl_post_reset
-    if (cnt > (unsigned)cap_seg) return;                     // overflow: reported through meta[], caller re-runs
     const int n = (int)cnt;
     uint4 *rec = cand + (size_t)seg * cap_seg;
     const float4 *boxes = boxtab + (size_t)b * M;
@@ -251,6 +383,8 @@ k_segment_nms(uint4 *__restrict__ cand, const unsigned *__restrict__ seg_count, 
             __syncthreads();
         }
         if (tid == 0) kept_count[seg] = (unsigned)nk;
+    }
+    __syncthreads();
     }
 }
 
@@ -322,9 +456,17 @@ extern "C" int yl_nms(void *ws, size_t ws_bytes, int B, long M, int C, int cap_s
     const float *objtab = (const float *)(w + L.off_obj);
     unsigned *kept_scratch = (cap_seg > SMEM_R) ? (unsigned *)(w + L.off_kept_scratch) : nullptr;
     const int nseg = img_count * C, seg_first = img_first * C;
-    k_segment_nms<<<nseg, NMS_THREADS, 0, (cudaStream_t)stream>>>(cand, seg_count, kept_count, boxtab, M, C, cap_seg,
-                                                                nms_thre, seg_first, kept_scratch);
+    unsigned *big_count = (unsigned *)(w + L.off_big_count) + img_first;
+    unsigned *big_list = (unsigned *)(w + L.off_big_list) + seg_first;
+    k_segment_nms_small<<<nseg, SMALL_THREADS, 0, (cudaStream_t)stream>>>(cand, seg_count, kept_count, boxtab, M, C, cap_seg,
+                                                                        nms_thre, seg_first, big_count, big_list);
     YL_LAUNCH_CHECK();
+    if (cap_seg > SMALL_R) {
+        const int grid_big = nseg < 148 * 2 ? nseg : 148 * 2;
+        k_segment_nms_big<<<grid_big, NMS_THREADS, 0, (cudaStream_t)stream>>>(cand, seg_count, kept_count, boxtab, M, C, cap_seg,
+                                                                             nms_thre, big_count, big_list, kept_scratch);
+        YL_LAUNCH_CHECK();
+    }
     k_gather_rows<<<nseg, GATHER_THREADS, 0, (cudaStream_t)stream>>>(cand, seg_count, kept_count, boxtab, objtab, M, C,
                                                                    cap_seg, B, out_rows, cap_out, meta, seg_first);
     YL_LAUNCH_CHECK();
