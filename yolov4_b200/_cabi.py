@@ -25,7 +25,7 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB
+    path = os.environ.get("YL_LIB", _build.LIB)      # YL_LIB: load a tuning build instead of the default library
     if not os.path.exists(path):
         # build from source if a toolchain is present; otherwise fail loudly (never fall back to eager PyTorch)
         path = _build.build_lib()

@@ -38,8 +38,9 @@ def is_stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_lib(force=False, verbose=False):
-    if not force and not is_stale():
+def build_lib(force=False, verbose=False, extra=(), out=None):
+    """extra: additional nvcc flags (e.g. -DYL_WT_STAGES=3 for tuning builds); out: alternative output path."""
+    if out is None and not force and not is_stale():
         return LIB
     objs = []
     bdir = os.path.join(HERE, "build")
@@ -47,18 +48,20 @@ def build_lib(force=False, verbose=False):
     procs = []
     for src in sources():
         obj = os.path.join(bdir, os.path.basename(src)[:-3] + ".o")
-        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        if out is not None:
+            obj = obj[:-2] + "." + os.path.basename(out) + ".o"
+        cmd = [_nvcc()] + NVCC_FLAGS + list(extra) + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     for cmd, p in procs:
-        out, _ = p.communicate()
-        if verbose and out:
-            print(out)
+        log, _ = p.communicate()
+        if verbose and log:
+            print(log)
         if p.returncode != 0:
-            raise RuntimeError("nvcc failed: %s\n%s" % (" ".join(cmd), out))
-    cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+            raise RuntimeError("nvcc failed: %s\n%s" % (" ".join(cmd), log))
+    cmd = [_nvcc(), "-shared", "-o", out or LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
     subprocess.check_call(cmd)
-    return LIB
+    return out or LIB
 
 
 if __name__ == "__main__":

@@ -7,6 +7,10 @@
 // Both append one record per surviving (box,class) pair to the (image,class) segment cand[(b*C+c)*cap_seg + slot]
 // and store the box once in boxtab/objtab[b*M + row].  Slot order inside a segment is arbitrary (atomics); the NMS
 // stage sorts by the unique key (score, row), so final results are deterministic.
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
+
 #include "yl_common.cuh"
 #include "../../include/yolo_head.h"
 
@@ -25,6 +29,12 @@ __device__ __forceinline__ float class_logit_bound(float obj, float thr)
     float q = fminf((thr / obj) * (1.0f - 1e-5f), 0.9f);
     const float L = __logf(q / (1.0f - q));
     return L - 0.01f - 1e-3f * fabsf(L);
+}
+
+// bits |= bit unless t < lth (NaN logits set the bit too): FSETP + predicated LOP3, the whole per-logit cost of phase 1.
+__device__ __forceinline__ void flag_or(unsigned &bits, float t, float lth, unsigned bit)
+{
+    asm("{\n\t.reg .pred p;\n\tsetp.lt.f32 p, %1, %2;\n\t@!p or.b32 %0, %0, %3;\n\t}" : "+r"(bits) : "f"(t), "f"(lth), "r"(bit));
 }
 
 // One scale of the head as the kernel sees it.
@@ -49,13 +59,13 @@ struct RawParams {
 };
 
 constexpr int K1_WARPS = K1_THREADS / 32;
-constexpr int K1_QCAP = 512;           // flagged (box,class) pairs a warp resolves cooperatively per tile
+constexpr int K1_QCAP = 256;           // flagged (box,class) pairs a warp resolves per batch (a box has at most 128)
 
-struct K1Smem {
-    unsigned short ent[K1_WARPS][K1_QCAP];   // bit15 pass | box slot (7b) << 8 | class (7b)
-    unsigned cls[K1_WARPS][K1_QCAP];         // sigmoid(class logit) bits of passing entries
-    float obj[K1_WARPS][128];
-    unsigned any[K1_WARPS][4], nan[K1_WARPS][4];
+// Per-warp scratch of the exact pass.
+struct EmitWarp {
+    unsigned short ent[K1_QCAP];       // bit15 pass | box slot (7b) << 8 | class (7b)
+    unsigned cls[K1_QCAP];             // sigmoid(class logit) bits of passing entries
+    unsigned any[4], nan[4];           // per box slot: has a surviving pair / has a NaN class logit
 };
 
 // Decode one box (yololayer.py:150-162) and convert to corners (utils.py:117-126).
@@ -71,19 +81,149 @@ __device__ __forceinline__ float4 decode_box(const float *bp, int F2, int Fw, in
     return make_float4(__fsub_rn(bx, hw), __fsub_rn(by, hh), __fadd_rn(bx, hw), __fadd_rn(by, hh));
 }
 
+// Exact pass over one batch of `total` queued (box slot, class) pairs of a warp tile.  All lanes take part:
+//   1. reload the flagged logits (all loads of a 128-entry round in flight together), exact spec-math test
+//   2. boxes with a surviving pair and no NaN class logit are decoded once (lane i takes the i-th such box)
+//   3. one record per surviving pair is appended to its (image, class) segment
+// sobj[slot] = sigmoid(objectness) of the warp tile's boxes; wbase = plane 0 of the (image, anchor) at the tile's first box.
+template <int VEC>
+__device__ __forceinline__ void emit_batch(const RawParams &P, const RawLayer &Ly, EmitWarp &E, const float *sobj,
+                                           const float *wbase, int b, int a, int wp0, int total)
+{
+    const int lane = threadIdx.x & 31;
+    const int C = P.C, F2 = Ly.F2;
+    const float thr = P.thr;
+    const float *wcp = wbase + 5 * (size_t)F2;
+    const int row_base = Ly.row_off + a * F2;                        // + p = row inside the image
+    __syncwarp();                                                    // queue entries and any/nan masks are visible
+    for (int e0 = 0; e0 < total; e0 += 128) {
+        float t[4];
+        unsigned en[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int q = e0 + 32 * u + lane;
+            en[u] = (q < total) ? E.ent[q] : 0u;
+            t[u] = (q < total) ? wcp[(size_t)(en[u] & 0x7F) * F2 + (en[u] >> 8)] : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int q = e0 + 32 * u + lane;
+            if (q < total) {
+                const int bs = en[u] >> 8;
+                // a NaN class logit makes torch.max (utils.py:139) NaN and drops the whole row (:145)
+                if (t[u] != t[u]) atomicOr(&E.nan[bs >> 5], 1u << (bs & 31));
+                const float cls = spec_sigmoidf(t[u]);
+                if (__fmul_rn(sobj[bs], cls) >= thr) {
+                    atomicOr(&E.any[bs >> 5], 1u << (bs & 31));
+                    E.cls[q] = __float_as_uint(cls);
+                    E.ent[q] = (unsigned short)(en[u] | 0x8000u);
+                }
+            }
+        }
+    }
+    __syncwarp();
+    {
+        unsigned lw[4];
+        int lc[4], nlive = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            lw[j] = (j < VEC) ? (E.any[j] & ~E.nan[j]) : 0u;
+            lc[j] = nlive;
+            nlive += __popc(lw[j]);
+        }
+        for (int i = lane; i < nlive; i += 32) {
+            int j = 0;
+#pragma unroll
+            for (int q = 1; q < 4; ++q) j = (i >= lc[q]) ? q : j;
+            const unsigned wsel = (j == 0) ? lw[0] : ((j == 1) ? lw[1] : ((j == 2) ? lw[2] : lw[3]));
+            const int lcs = (j == 0) ? lc[0] : ((j == 1) ? lc[1] : ((j == 2) ? lc[2] : lc[3]));
+            const int bs = 32 * j + (int)__fns(wsel, 0, i - lcs + 1);
+            const int p = wp0 + bs;
+            const size_t brow = (size_t)b * P.M + (row_base + p);
+            P.boxtab[brow] = decode_box(wbase + bs, F2, Ly.Fw, p, Ly.aw[a], Ly.ah[a], Ly.stride);
+            P.objtab[brow] = sobj[bs];
+        }
+    }
+    for (int q = lane; q < total; q += 32) {
+        const unsigned en = E.ent[q];
+        const int bs = (en >> 8) & 0x7F;
+        if ((en & 0x8000u) && !((E.nan[bs >> 5] >> (bs & 31)) & 1u)) {
+            const int k = en & 0x7F;
+            const float cls = __uint_as_float(E.cls[q]);
+            const float s = __fadd_rn(__fmul_rn(sobj[bs], cls), 0.0f);      // +0 canonicalises -0
+            const unsigned seg = (unsigned)(b * C + k);
+            const unsigned slot = atomicAdd(&P.seg_count[seg], 1u);
+            if (slot < (unsigned)P.cap_seg)
+                P.cand[(size_t)seg * P.cap_seg + slot] =
+                    make_uint4(__float_as_uint(s), (unsigned)(row_base + wp0 + bs), __float_as_uint(cls), 0u);
+        }
+    }
+    __syncwarp();
+    if (lane < 4) { E.any[lane] = 0u; E.nan[lane] = 0u; }
+}
+
+// Phase 2 of a warp tile (32*VEC consecutive boxes, lane L owns boxes L*VEC .. L*VEC+VEC-1, bits[v][w] = flagged classes):
+// the flag words are expanded into a queue of (box slot, class) pairs by the whole warp, box by box, and the
+// queue is resolved in batches of whole boxes.  sobj must already hold sigmoid(objectness) per box slot.
+template <int VEC, int NW>
+__device__ __forceinline__ void emit_pairs(const RawParams &P, const RawLayer &Ly, int ba, int wp0,
+                                           const float (&lth)[VEC], unsigned (&bits)[VEC][NW], EmitWarp &E, const float *sobj)
+{
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31;
+    const int b = ba / 3, a = ba - 3 * b;
+    const float *wbase = Ly.raw + ((size_t)ba * (5 + P.C)) * Ly.F2 + wp0;
+    unsigned flagged[VEC];
+    unsigned any_lane = 0u;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+        unsigned any = 0u;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) any |= bits[v][w];
+        if (lth[v] == kInf) any = 0u;
+        flagged[v] = __ballot_sync(FULL, any != 0u);
+        any_lane |= flagged[v];
+    }
+    if (any_lane == 0u) return;                                      // warp-uniform
+    if (lane < 4) { E.any[lane] = 0u; E.nan[lane] = 0u; }
+    int qb = 0;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+        unsigned lanes = flagged[v];
+        while (lanes) {                                              // warp-uniform loop over the flagged boxes
+            const int L = __ffs(lanes) - 1;
+            lanes &= lanes - 1;
+            unsigned m[NW];
+            int n = 0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) { m[w] = __shfl_sync(FULL, bits[v][w], L); n += __popc(m[w]); }
+            if (qb + n > K1_QCAP) { emit_batch<VEC>(P, Ly, E, sobj, wbase, b, a, wp0, qb); qb = 0; }
+            const unsigned hdr = (unsigned)(L * VEC + v) << 8;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                if ((m[w] >> lane) & 1u) E.ent[qb + __popc(m[w] & ((1u << lane) - 1u))] = (unsigned short)(hdr | (32 * w + lane));
+                qb += __popc(m[w]);
+            }
+        }
+    }
+    if (qb) emit_batch<VEC>(P, Ly, E, sobj, wbase, b, a, wp0, qb);
+}
+
 // One tile = K1_THREADS*VEC consecutive boxes of one (image, anchor).  Phase 1 streams the class planes with one
 // compare per logit; phase 2 resolves the ~1% flagged pairs warp-cooperatively (all lanes, all loads in flight
 // together) instead of serially in the lane that owns the box.
+struct LdgSmem {
+    EmitWarp e[K1_WARPS];
+    float sobj[K1_WARPS][128];
+};
+
 template <int VEC, int NW>
-__device__ __forceinline__ void filter_tile(const RawParams &P, const RawLayer &Ly, int tile, int ba, K1Smem &sm)
+__device__ __forceinline__ void filter_tile(const RawParams &P, const RawLayer &Ly, int tile, int ba, LdgSmem &sm)
 {
-    const unsigned FULL = 0xFFFFFFFFu;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int C = P.C, F2 = Ly.F2;
     const float thr = P.thr;
     const int p0 = (tile * K1_THREADS + threadIdx.x) * VEC;
     const bool inb = p0 < F2;                                        // F2 % VEC == 0, so a vector is all in or all out
-    const int b = ba / 3, a = ba - 3 * b;
     const int nch = 5 + C;
     const float *base = Ly.raw + ((size_t)ba * nch) * F2 + (inb ? p0 : 0);
     const float *cp = base + 5 * (size_t)F2;
@@ -114,167 +254,222 @@ __device__ __forceinline__ void filter_tile(const RawParams &P, const RawLayer &
 #pragma unroll
         for (int w = 0; w < NW; ++w) {
             const int kn = min(32, C - 32 * w);
+#pragma unroll
+            for (int kk = 0; kk < 32; kk += 8) {                     // fully unrolled: every bit mask is an immediate
+                if (kk < kn) {
+                    Vec<VEC> t[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        if (kk + u < kn) t[u].load(cp + (size_t)(32 * w + kk + u) * F2);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        if (kk + u < kn) {
+#pragma unroll
+                            for (int v = 0; v < VEC; ++v) flag_or(bits[v][w], t[u].v[v], lth[v], 1u << (kk + u));
+                        }
+                }
+            }
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) sm.sobj[warp][lane * VEC + v] = obj[v];
+    emit_pairs<VEC, NW>(P, Ly, ba, (tile * K1_THREADS + warp * 32) * VEC, lth, bits, sm.e[warp], sm.sobj[warp]);
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// TMA form of the streaming pass (scales whose planes are 16-byte aligned: 76/38 @608, 52/26 @416).
+//
+// Every warp is an independent pipeline over "warp tiles" (128 consecutive boxes of one (image, anchor) x all
+// planes), fetched from a global atomic counter.  Lane 0 issues cp.async.bulk copies (SASS UBLKCP) of
+// [WT_KC class planes x 512 B] into the warp's private ring of shared-memory stages; each stage has a
+// transaction mbarrier the warp waits on.  A stage is refilled as soon as the warp has read it, and the ring keeps
+// running into the NEXT tile, so the next tile's first chunks (and its objectness plane) land while the warp
+// resolves the current tile's flagged pairs.  Bytes in flight are set by shared memory (12 warps x 12 KB per SM),
+// not by registers, and no warp ever waits for another.  Only the planes the pass needs are streamed: objectness
+// and the classes; tx,ty,tw,th are fetched on demand for the few boxes that produce a candidate.
+// ---------------------------------------------------------------------------------------------------------------
+#ifndef YL_WT_KC
+#define YL_WT_KC 8
+#endif
+#ifndef YL_WT_STAGES
+#define YL_WT_STAGES 2
+#endif
+constexpr int WT_KC = YL_WT_KC;            // class planes per stage
+constexpr int WT_STAGES = YL_WT_STAGES;
+constexpr int WT_BOX = 128;                // boxes per warp tile (32 lanes x float4)
+
+struct alignas(128) WtWarp {
+    float stage[WT_STAGES][WT_KC][WT_BOX];     // 12 KB
+    float objp[2][WT_BOX];                     // objectness plane of the current / the next tile
+    unsigned long long full[WT_STAGES], obj_full[2];
+    EmitWarp em;
+};
+struct WtSmem {
+    WtWarp w[K1_WARPS];
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    unsigned ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// 2-D tiled TMA load (SASS UTMALDG): box [WT_KC planes x WT_BOX boxes] at (column x, plane row y) of a scale's
+// [B*3*(5+C) planes, F*F] view.  Out-of-range columns/rows are zero-filled and still count as transferred bytes.
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int x, int y, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
+}
+
+struct TmaMaps { CUtensorMap m[3]; };
+
+struct WtTile {
+    const float *src;      // plane 0 of this (image, anchor) at the tile's first box
+    int layer, ba, p0, np; // np = boxes in the tile (<= 128, multiple of 4); np == 0: no tile
+    int row0;              // plane row of class 0 in the scale's 2-D view: ba*(5+C) + 5
+};
+
+// P.layer[] holds only the TMA-capable scales; layer[l].tiles = ceil(F2 / WT_BOX) warp tiles per (image, anchor).
+__device__ __forceinline__ WtTile wt_tile(const RawParams &P, int t, int n_tiles, int nba)
+{
+    WtTile T;
+    T.np = 0; T.src = nullptr; T.layer = 0; T.ba = 0; T.p0 = 0; T.row0 = 0;
+    if (t >= n_tiles) return T;
+    int l = 0;
+    while (l < P.n_layers - 1 && t >= P.layer[l].tiles * nba) { t -= P.layer[l].tiles * nba; ++l; }
+    const int tp = P.layer[l].tiles;
+    const int bal = t / tp, tx = t - bal * tp;
+    T.layer = l;
+    T.ba = P.img_first * 3 + bal;
+    T.p0 = tx * WT_BOX;
+    T.np = min(WT_BOX, P.layer[l].F2 - T.p0);
+    T.src = P.layer[l].raw + ((size_t)T.ba * (5 + P.C)) * P.layer[l].F2 + T.p0;
+    T.row0 = T.ba * (5 + P.C) + 5;
+    return T;
+}
+
+template <int NW>
+__global__ void __launch_bounds__(K1_THREADS)
+k_filter_raw_tma(const __grid_constant__ RawParams P, const __grid_constant__ TmaMaps maps, int nba, int n_tiles,
+                 unsigned *__restrict__ tile_counter)
+{
+    extern __shared__ __align__(128) unsigned char wt_smem_raw[];
+    WtSmem &S = *reinterpret_cast<WtSmem *>(wt_smem_raw);
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WtWarp &W = S.w[warp];
+    const int C = P.C;
+    const int n_cc = (C + WT_KC - 1) / WT_KC;                        // class chunks per tile
+
+    if (lane == 0) {
+        for (int s = 0; s < WT_STAGES; ++s) mbar_init(&W.full[s], 1);
+        mbar_init(&W.obj_full[0], 1);
+        mbar_init(&W.obj_full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+
+    // lane 0 issues one class chunk of tile T into ring stage s
+    auto issue_chunk = [&](const WtTile &T, int c, int s) {
+        mbar_expect_tx(&W.full[s], WT_KC * WT_BOX * 4u);             // full box, zero fill included
+        tma_load_2d(&W.stage[s][0][0], &maps.m[T.layer], T.p0, T.row0 + c * WT_KC, &W.full[s]);
+    };
+    auto issue_obj = [&](const WtTile &T, int slot) {
+        const unsigned bytes = (unsigned)T.np * 4u;
+        mbar_expect_tx(&W.obj_full[slot], bytes);
+        bulk_g2s(&W.objp[slot][0], T.src + 4 * (size_t)P.layer[T.layer].F2, bytes, &W.obj_full[slot]);
+    };
+    auto fetch_tile = [&]() {
+        int t = 0;
+        if (lane == 0) t = (int)atomicAdd(tile_counter, 1u);
+        return wt_tile(P, __shfl_sync(FULL, t, 0), n_tiles, nba);
+    };
+
+    WtTile cur = fetch_tile();
+    if (cur.np == 0) return;
+    if (lane == 0) {
+        issue_obj(cur, 0);
+        for (int c = 0; c < WT_STAGES && c < n_cc; ++c) issue_chunk(cur, c, c);
+    }
+    int s = 0;                       // ring stage of the next chunk to consume
+    unsigned ph = 0u;                // phase bit per ring stage
+    unsigned it = 0u;                // tiles processed by this warp (objectness slot = it & 1, phase = (it >> 1) & 1)
+
+    while (cur.np != 0) {
+        const WtTile nxt = fetch_tile();
+        if (lane == 0 && nxt.np != 0) issue_obj(nxt, (it + 1) & 1);
+        const RawLayer &Ly = P.layer[cur.layer];
+        const bool inb = lane * 4 < cur.np;
+        float obj[4], lth[4];
+        {
+            mbar_wait(&W.obj_full[it & 1], (it >> 1) & 1u);
+            const float4 to = *reinterpret_cast<const float4 *>(&W.objp[it & 1][lane * 4]);
+            const float tv[4] = {to.x, to.y, to.z, to.w};
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                obj[v] = inb ? spec_sigmoidf(tv[v]) : 0.0f;
+                lth[v] = inb ? class_logit_bound(obj[v], P.thr) : kInf;
+            }
+        }
+        unsigned bits[4][NW];
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            unsigned m0 = 0u, m1 = 0u, m2 = 0u, m3 = 0u;
 #pragma unroll 1
-            for (int kk = 0; kk < kn; kk += 8) {
-                Vec<VEC> t[8];
+            for (int cc = 0; cc < 32 / WT_KC; ++cc) {
+                const int c = w * (32 / WT_KC) + cc;                 // class chunk index
+                if (c >= n_cc) break;                                // warp-uniform
+                mbar_wait(&W.full[s], (ph >> s) & 1u);
+                const int kn = min(WT_KC, C - c * WT_KC);
+                const float *sp = &W.stage[s][0][lane * 4];
+                unsigned a0 = 0u, a1 = 0u, a2 = 0u, a3 = 0u;
 #pragma unroll
-                for (int u = 0; u < 8; ++u)
-                    if (kk + u < kn) t[u].load(cp + (size_t)(32 * w + kk + u) * F2);
-#pragma unroll
-                for (int u = 0; u < 8; ++u)
-                    if (kk + u < kn) {
-#pragma unroll
-                        for (int v = 0; v < VEC; ++v)
-                            bits[v][w] |= (t[u].v[v] < lth[v]) ? 0u : (1u << (kk + u));   // NaN logits set the bit too
+                for (int k = 0; k < WT_KC; ++k)
+                    if (k < kn) {
+                        const float4 tv = *reinterpret_cast<const float4 *>(sp + k * WT_BOX);
+                        flag_or(a0, tv.x, lth[0], 1u << k);
+                        flag_or(a1, tv.y, lth[1], 1u << k);
+                        flag_or(a2, tv.z, lth[2], 1u << k);
+                        flag_or(a3, tv.w, lth[3], 1u << k);
                     }
-            }
-        }
-    }
-    int cnt = 0;
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) {
-        if (lth[v] == kInf) {
-#pragma unroll
-            for (int w = 0; w < NW; ++w) bits[v][w] = 0u;
-        }
-#pragma unroll
-        for (int w = 0; w < NW; ++w) cnt += __popc(bits[v][w]);
-    }
-    int incl = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int n = __shfl_up_sync(FULL, incl, o);
-        if (lane >= o) incl += n;
-    }
-    const int total = __shfl_sync(FULL, incl, 31);
-    if (total == 0) return;                                          // warp-uniform
-
-    const float aw = Ly.aw[a], ah = Ly.ah[a];
-    const int row_base = Ly.row_off + a * F2;                        // + p = row inside the image
-    if (total <= K1_QCAP) {
-        // ---- phase 2: cooperative exact pass ------------------------------------------------------------------
-        unsigned short *ent = sm.ent[warp];
-        unsigned *ecls = sm.cls[warp];
-        int e = incl - cnt;
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-            sm.obj[warp][lane * VEC + v] = obj[v];
-#pragma unroll
-            for (int w = 0; w < NW; ++w) {
-                unsigned m = bits[v][w];
-                while (m) {
-                    const int bit = __ffs(m) - 1;
-                    m &= m - 1;
-                    ent[e++] = (unsigned short)(((lane * VEC + v) << 8) | (32 * w + bit));
+                const int sh = cc * WT_KC;
+                m0 |= a0 << sh; m1 |= a1 << sh; m2 |= a2 << sh; m3 |= a3 << sh;
+                __syncwarp();                                        // every lane has read the stage
+                if (lane == 0) {
+                    const int cn = c + WT_STAGES;                    // the chunk that takes this stage next
+                    if (cn < n_cc) issue_chunk(cur, cn, s);
+                    else if (nxt.np != 0 && cn - n_cc < n_cc) issue_chunk(nxt, cn - n_cc, s);
                 }
+                ph ^= 1u << s;
+                s = (s + 1 == WT_STAGES) ? 0 : s + 1;
             }
+            bits[0][w] = m0; bits[1][w] = m1; bits[2][w] = m2; bits[3][w] = m3;
         }
-        if (lane < 4) { sm.any[warp][lane] = 0u; sm.nan[warp][lane] = 0u; }
-        __syncwarp();
-        const int wp0 = __shfl_sync(FULL, p0, 0);                    // first box of the warp (lane 0 is in bounds when total > 0)
-        const float *wbase = Ly.raw + ((size_t)ba * nch) * F2 + wp0;
-        const float *wcp = wbase + 5 * (size_t)F2;
-        for (int e0 = 0; e0 < total; e0 += 128) {
-            float t[4];
-            unsigned en[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int q = e0 + 32 * u + lane;
-                en[u] = (q < total) ? ent[q] : 0xFFFFu;
-                t[u] = (q < total) ? wcp[(size_t)(en[u] & 0x7F) * F2 + (en[u] >> 8)] : 0.0f;
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int q = e0 + 32 * u + lane;
-                if (q < total) {
-                    const int bs = en[u] >> 8;
-                    // a NaN class logit makes torch.max (utils.py:139) NaN and drops the whole row (:145)
-                    if (t[u] != t[u]) atomicOr(&sm.nan[warp][bs >> 5], 1u << (bs & 31));
-                    const float cls = spec_sigmoidf(t[u]);
-                    if (__fmul_rn(sm.obj[warp][bs], cls) >= thr) {
-                        atomicOr(&sm.any[warp][bs >> 5], 1u << (bs & 31));
-                        ecls[q] = __float_as_uint(cls);
-                        ent[q] = (unsigned short)(en[u] | 0x8000u);
-                    }
-                }
-            }
-        }
-        __syncwarp();
-        // boxes with at least one surviving pair: decode once, store corners + objectness
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) {
-            const int bs = lane + 32 * j;
-            const unsigned live = (sm.any[warp][bs >> 5] & ~sm.nan[warp][bs >> 5]) >> (bs & 31) & 1u;
-            if (live) {
-                const int p = wp0 + bs;
-                const size_t brow = (size_t)b * P.M + (row_base + p);
-                P.boxtab[brow] = decode_box(wbase + bs, F2, Ly.Fw, p, aw, ah, Ly.stride);
-                P.objtab[brow] = sm.obj[warp][bs];
-            }
-        }
-        // one record per surviving (box,class) pair
-        for (int q = lane; q < total; q += 32) {
-            const unsigned en = ent[q];
-            const int bs = (en >> 8) & 0x7F;
-            if ((en & 0x8000u) && !((sm.nan[warp][bs >> 5] >> (bs & 31)) & 1u)) {
-                const int k = en & 0x7F;
-                const float cls = __uint_as_float(ecls[q]);
-                const float s = __fadd_rn(__fmul_rn(sm.obj[warp][bs], cls), 0.0f);      // +0 canonicalises -0
-                const unsigned seg = (unsigned)(b * C + k);
-                const unsigned slot = atomicAdd(&P.seg_count[seg], 1u);
-                if (slot < (unsigned)P.cap_seg)
-                    P.cand[(size_t)seg * P.cap_seg + slot] =
-                        make_uint4(__float_as_uint(s), (unsigned)(row_base + wp0 + bs), __float_as_uint(cls), 0u);
-            }
-        }
-        __syncwarp();
-        return;
-    }
-
-    // ---- dense fallback (more than K1_QCAP flagged pairs in the warp: degenerate inputs): per-lane serial pass ------
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) {
-        unsigned any = 0u;
-#pragma unroll
-        for (int w = 0; w < NW; ++w) any |= bits[v][w];
-        if (!any) continue;
-        bool nan_row = false;
-#pragma unroll
-        for (int w = 0; w < NW; ++w) {
-            unsigned m = bits[v][w];
-            while (m) {
-                const int bit = __ffs(m) - 1;
-                m &= m - 1;
-                const float t = cp[(size_t)(32 * w + bit) * F2 + v];
-                nan_row |= (t != t);
-                if (!(__fmul_rn(obj[v], spec_sigmoidf(t)) >= thr)) bits[v][w] &= ~(1u << bit);
-            }
-        }
-        if (nan_row) continue;
-        any = 0u;
-#pragma unroll
-        for (int w = 0; w < NW; ++w) any |= bits[v][w];
-        if (!any) continue;
-        const int p = p0 + v;
-        const unsigned row = (unsigned)(row_base + p);
-        const size_t brow = (size_t)b * P.M + row;
-        P.boxtab[brow] = decode_box(base + v, F2, Ly.Fw, p, aw, ah, Ly.stride);
-        P.objtab[brow] = obj[v];
-#pragma unroll
-        for (int w = 0; w < NW; ++w) {
-            unsigned m = bits[v][w];
-            while (m) {
-                const int bit = __ffs(m) - 1;
-                m &= m - 1;
-                const int k = 32 * w + bit;
-                const float cls = spec_sigmoidf(cp[(size_t)k * F2 + v]);
-                const float s = __fadd_rn(__fmul_rn(obj[v], cls), 0.0f);
-                const unsigned seg = (unsigned)(b * C + k);
-                const unsigned slot = atomicAdd(&P.seg_count[seg], 1u);
-                if (slot < (unsigned)P.cap_seg)
-                    P.cand[(size_t)seg * P.cap_seg + slot] = make_uint4(__float_as_uint(s), row, __float_as_uint(cls), 0u);
-            }
-        }
+        // sigmoid(objectness) replaces the logits in the tile's objectness slot: the exact pass reads it per box slot
+        *reinterpret_cast<float4 *>(&W.objp[it & 1][lane * 4]) = make_float4(obj[0], obj[1], obj[2], obj[3]);
+        emit_pairs<4, NW>(P, Ly, cur.ba, cur.p0, lth, bits, W.em, W.objp[it & 1]);
+        cur = nxt;
+        ++it;
     }
 }
 
@@ -283,7 +478,7 @@ template <int NW>
 __global__ void __launch_bounds__(K1_THREADS)
 k_filter_raw(const __grid_constant__ RawParams P)
 {
-    __shared__ K1Smem sm;
+    __shared__ LdgSmem sm;
     const int ba = P.img_first * 3 + blockIdx.y;
     int tile = blockIdx.x;
     int l = 0;
@@ -364,6 +559,38 @@ k_filter_dense(const float *__restrict__ pred, long M, int C, int num_classes, f
 
 using namespace yl;
 
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// YL_NO_TMA=1 forces the register-staged LDG kernel for every scale (A/B measurements).
+static const bool g_use_tma = !(getenv("YL_NO_TMA") && getenv("YL_NO_TMA")[0] == '1');
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda).
+static int encode_plane_map(CUtensorMap *map, const float *raw, int F2, long rows)
+{
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) return YL_ERR_CUDA_BASE + (int)cudaErrorNotSupported;
+        fn = (PFN_encodeTiled)p;
+    }
+    const cuuint64_t gdim[2] = {(cuuint64_t)F2, (cuuint64_t)rows};
+    const cuuint64_t gstr[1] = {(cuuint64_t)F2 * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)WT_BOX, (cuuint32_t)WT_KC};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)raw, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? YL_OK : YL_ERR_CUDA_BASE + (int)cudaErrorInvalidValue;
+}
+
+static int g_num_sms()
+{
+    static int n = 0;
+    if (!n) { int dev = 0; cudaGetDevice(&dev); if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148; }
+    return n;
+}
+
 extern "C" size_t yl_post_workspace_bytes(int B, long M, int C, int cap_seg)
 {
     if (B <= 0 || M <= 0 || C <= 0 || cap_seg <= 0) return 0;
@@ -399,13 +626,13 @@ extern "C" int yl_filter_raw(const float *const *raw, const int *F, int n_layers
     uint4 *cand = (uint4 *)(w + L.off_cand);
     float4 *boxtab = (float4 *)(w + L.off_box);
     float *objtab = (float *)(w + L.off_obj);
-    RawParams P;
-    P.n_layers = n_layers; P.C = C; P.cap_seg = cap_seg; P.img_first = img_first; P.M = M; P.thr = conf_thre;
-    P.cand = cand; P.seg_count = seg_count; P.boxtab = boxtab; P.objtab = objtab;
-    int row_off = 0, tiles_total = 0;
-    for (int l = 0; l < 3; ++l) {
-        RawLayer &Ly = P.layer[l];
-        if (l >= n_layers) { Ly = P.layer[0]; Ly.tiles = 0; continue; }
+    RawParams base;
+    base.C = C; base.cap_seg = cap_seg; base.img_first = img_first; base.M = M; base.thr = conf_thre;
+    base.cand = cand; base.seg_count = seg_count; base.boxtab = boxtab; base.objtab = objtab; base.n_layers = 0;
+    RawParams Pt = base, Pl = base;                                          // TMA-capable scales / the rest (LDG)
+    int row_off = 0, tiles_tma = 0, tiles_ldg = 0;
+    for (int l = 0; l < n_layers; ++l) {
+        RawLayer Ly;
         Ly.raw = raw[l]; Ly.Fw = F[l]; Ly.F2 = F[l] * F[l]; Ly.row_off = row_off;
         Ly.stride = (float)(8 << l);                                        // yololayer.py:54
         for (int a = 0; a < 3; ++a) {                                       // yololayer.py:73-76 (doubles, then fp32)
@@ -414,22 +641,61 @@ extern "C" int yl_filter_raw(const float *const *raw, const int *F, int n_layers
             Ly.aw[a] = (float)((double)anchors_px[2 * q] / (double)Ly.stride);
             Ly.ah[a] = (float)((double)anchors_px[2 * q + 1] / (double)Ly.stride);
         }
-        // 128-bit loads need 16-byte aligned planes: F^2 % 4 == 0 and an aligned base (19x19 / 13x13 grids fall back)
+        // 128-bit loads / bulk copies need 16-byte aligned planes: F^2 % 4 == 0 and an aligned base (19x19, 13x13 fall back)
         Ly.vec = ((Ly.F2 % 4 == 0) && (((uintptr_t)raw[l]) % 16 == 0)) ? 4 : 1;
-        Ly.tiles = (Ly.F2 / Ly.vec + K1_THREADS - 1) / K1_THREADS;
-        tiles_total += Ly.tiles;
+        if (Ly.vec == 4 && g_use_tma && (C + WT_KC - 1) / WT_KC >= WT_STAGES) {
+            Ly.tiles = (Ly.F2 + WT_BOX - 1) / WT_BOX;
+            tiles_tma += Ly.tiles;
+            Pt.layer[Pt.n_layers++] = Ly;
+        } else {
+            Ly.tiles = (Ly.F2 / Ly.vec + K1_THREADS - 1) / K1_THREADS;
+            tiles_ldg += Ly.tiles;
+            Pl.layer[Pl.n_layers++] = Ly;
+        }
         row_off += 3 * Ly.F2;
     }
-    dim3 grid(tiles_total, img_count * 3);
+    for (int l = Pt.n_layers; l < 3; ++l) { Pt.layer[l] = Pt.layer[0]; Pt.layer[l].tiles = 0; }
+    for (int l = Pl.n_layers; l < 3; ++l) { Pl.layer[l] = Pl.layer[0]; Pl.layer[l].tiles = 0; }
     cudaStream_t st = (cudaStream_t)stream;
-    switch ((C + 31) / 32) {
-    case 1: k_filter_raw<1><<<grid, K1_THREADS, 0, st>>>(P); break;
-    case 2: k_filter_raw<2><<<grid, K1_THREADS, 0, st>>>(P); break;
-    case 3: k_filter_raw<3><<<grid, K1_THREADS, 0, st>>>(P); break;
-    case 4: k_filter_raw<4><<<grid, K1_THREADS, 0, st>>>(P); break;
-    default: return YL_ERR_CLASSES;
+    const int NW = (C + 31) / 32;
+    if (NW < 1 || NW > 4) return YL_ERR_CLASSES;
+    if (Pt.n_layers > 0) {
+        const int nba = img_count * 3;
+        const int n_tiles = nba * tiles_tma;                                 // warp tiles
+        const size_t smem = sizeof(WtSmem);
+        const int ctas_per_sm = (int)((227 * 1024) / (smem + 1024));
+        const int want = (n_tiles + K1_WARPS - 1) / K1_WARPS;
+        const int grid = want < ctas_per_sm * g_num_sms() ? want : ctas_per_sm * g_num_sms();
+        unsigned *tile_counter = (unsigned *)(w + L.off_tile_count) + img_first;
+        TmaMaps maps;
+        memset(&maps, 0, sizeof(maps));
+        for (int l = 0; l < Pt.n_layers; ++l) {
+            const int rc = encode_plane_map(&maps.m[l], Pt.layer[l].raw, Pt.layer[l].F2, (long)B * 3 * (5 + C));
+            if (rc != YL_OK) return rc;
+        }
+#define YL_TMA_CASE(NW_)                                                                                             \
+    case NW_: {                                                                                                      \
+        static bool attr_done = false;                                                                               \
+        if (!attr_done) {                                                                                            \
+            YL_CUDA_TRY(cudaFuncSetAttribute(k_filter_raw_tma<NW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            attr_done = true;                                                                                        \
+        }                                                                                                            \
+        k_filter_raw_tma<NW_><<<grid, K1_THREADS, smem, st>>>(Pt, maps, nba, n_tiles, tile_counter);                       \
+    } break;
+        switch (NW) { YL_TMA_CASE(1) YL_TMA_CASE(2) YL_TMA_CASE(3) YL_TMA_CASE(4) }
+#undef YL_TMA_CASE
+        YL_LAUNCH_CHECK();
     }
-    YL_LAUNCH_CHECK();
+    if (Pl.n_layers > 0) {
+        dim3 grid(tiles_ldg, img_count * 3);
+        switch (NW) {
+        case 1: k_filter_raw<1><<<grid, K1_THREADS, 0, st>>>(Pl); break;
+        case 2: k_filter_raw<2><<<grid, K1_THREADS, 0, st>>>(Pl); break;
+        case 3: k_filter_raw<3><<<grid, K1_THREADS, 0, st>>>(Pl); break;
+        default: k_filter_raw<4><<<grid, K1_THREADS, 0, st>>>(Pl); break;
+        }
+        YL_LAUNCH_CHECK();
+    }
     return YL_OK;
 }
 
