@@ -29,3 +29,18 @@ for r, (off, src, txt) in zip(data, lines):
 print("total warp-instr %d samples %d" % tuple(tot))
 for src, (e, s) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:45]:
     print("%-22s exec %5.1f%%  samples %5.1f%%" % ("%s:%d" % src if src else "?", 100 * e / tot[0], 100 * s / max(tot[1], 1)))
+
+if len(sys.argv) > 4 and sys.argv[4] == "stalls":
+    names = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
+    idx = [hdr.index(h) for h in names]
+    per = collections.defaultdict(lambda: collections.Counter())
+    for r, (off, src, txt) in zip(data, lines):
+        for h, i in zip(names, idx):
+            try:
+                per[src][h] += int(r[i])
+            except Exception:
+                pass
+    print("--- by samples")
+    for src, (e, s_) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:25]:
+        top = ", ".join("%s %d" % (k.replace("stall_", ""), v) for k, v in per[src].most_common(3))
+        print("%-22s samples %5.1f%%  exec %5.1f%%   %s" % ("%s:%d" % src if src else "?", 100 * s_ / max(tot[1], 1), 100 * e / tot[0], top))

@@ -8,6 +8,8 @@
 //
 // Segments up to SMEM_R candidates are processed entirely in shared memory; larger ones (degenerate inputs
 // such as the all-ties random-init case) run the same algorithm in place in global memory.
+#include <stdlib.h>
+
 #include "yl_common.cuh"
 #include "../../include/yolo_head.h"
 
@@ -26,8 +28,15 @@ __device__ __forceinline__ bool suppresses_pos(const float4 &a, float area_a, co
     const float brx = fminf(a.z, b.z), bry = fminf(a.w, b.w);
     if (!(tlx < brx && tly < bry)) return false;
     const float inter = __fmul_rn(__fsub_rn(brx, tlx), __fsub_rn(bry, tly));
-    const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
-    return iou >= thr;
+    const float uni = __fsub_rn(__fadd_rn(area_a, area_b), inter);
+    // fl(inter/uni) >= thr is decided without the division when inter is not within 0.1% of thr*uni (the quotient's
+    // rounding error is 6e-8): only the rare near-threshold pair pays for the IEEE divide.
+    if (uni > 0.0f && uni < 3.0e38f) {
+        const float tu = thr * uni;
+        if (inter < 0.999f * tu) return false;
+        if (inter > 1.001f * tu && inter < 3.0e38f) return true;
+    }
+    return __fdiv_rn(inter, uni) >= thr;
 }
 
 // General path (thr <= 0 or unsanitised boxes): literal NaN-propagating formula.
@@ -193,22 +202,77 @@ constexpr int SMALL_R = 256;
 constexpr int SMALL_W = SMALL_R / 32;
 constexpr int SMALL_THREADS = 128;
 
-template <bool POS>
-__device__ __forceinline__ void small_pairs(const float4 *sh_box, const float *sh_area, unsigned (*sh_T)[SMALL_W + 1], int n, float thr)
+// Conservative 16-bit image of a (sanitised) box for the pair prefilter: corners are rounded outwards (floor for x1,y1,
+// ceil for x2,y2), clamped to +-16384 px and biased to 15-bit unsigned, two per 32-bit word.  Rounding and clamping are
+// monotone, so  true overlap (tl < br on both axes)  =>  q(tl) <= q(br) on both axes : the integer test never rejects
+// a pair the exact fp32 test would accept.  A NaN box (sanitised to +inf/-inf) maps to lo=32767 > hi=0: never overlaps.
+__device__ __forceinline__ uint2 quantise_box(const float4 &b)
 {
-    for (int j = threadIdx.x; j < n; j += SMALL_THREADS) {
-        const float4 bj = sh_box[j];
-        const float aj = sh_area[j];
-#pragma unroll
-        for (int w = 0; w < SMALL_W; ++w) {
+    const int x1 = min(max(__float2int_rd(fminf(fmaxf(b.x, -16384.0f), 16383.0f)), -16384), 16383) + 16384;
+    const int y1 = min(max(__float2int_rd(fminf(fmaxf(b.y, -16384.0f), 16383.0f)), -16384), 16383) + 16384;
+    const int x2 = min(max(__float2int_ru(fminf(fmaxf(b.z, -16384.0f), 16383.0f)), -16384), 16383) + 16384;
+    const int y2 = min(max(__float2int_ru(fminf(fmaxf(b.w, -16384.0f), 16383.0f)), -16384), 16383) + 16384;
+    return make_uint2((unsigned)x1 | ((unsigned)y1 << 16), (unsigned)x2 | ((unsigned)y2 << 16));
+}
+
+// (br + 0x8000 - tl) per 16-bit half never borrows or overflows for 15-bit operands; bit 15 of a half is set iff br >= tl.
+__device__ __forceinline__ bool may_overlap(const uint2 &a, const uint2 &b)
+{
+    const unsigned tl = __vmaxu2(a.x, b.x), br = __vminu2(a.y, b.y);
+    return ((br + 0x80008000u - tl) & 0x80008000u) == 0x80008000u;
+}
+
+// Row j of the transposed suppression matrix: bit i (i < j) set when box i suppresses box j.
+// Number of keys below `key` (keys are unique): LDS.128 per two keys, one 64-bit compare + predicated add per key.
+__device__ __forceinline__ int rank_of(const unsigned long long *sh_key, int n, unsigned long long key)
+{
+    int r = 0;
+    const ulonglong2 *k2 = reinterpret_cast<const ulonglong2 *>(sh_key);
+    const int n2 = (n + 1) >> 1;
+#pragma unroll 4
+    for (int j = 0; j < n2; ++j) {
+        const ulonglong2 k = k2[j];
+        asm("{\n\t.reg .pred p, q;\n\tsetp.lt.u64 p, %1, %3;\n\tsetp.lt.u64 q, %2, %3;\n\t@p add.s32 %0, %0, 1;\n\t@q add.s32 %0, %0, 1;\n\t}"
+            : "+r"(r) : "l"(k.x), "l"(k.y), "l"(key));
+    }
+    return r;
+}
+
+template <bool POS>
+__device__ __forceinline__ void small_pairs(const float4 *sh_box, const float *sh_area, const uint2 *sh_q,
+                                            unsigned (*sh_T)[SMALL_W + 1], int n, float thr)
+{
+    for (int j0 = 0; j0 < n; j0 += SMALL_THREADS) {
+        const int j = j0 + (int)threadIdx.x;
+        const int jw = (j0 + ((int)threadIdx.x & ~31)) >> 5;        // word of this warp's rows (warp-uniform)
+        if (32 * jw >= n) break;                                     // the whole warp is past the segment
+        const bool have = j < n;
+        const float4 bj = sh_box[have ? j : 0];
+        const float aj = sh_area[have ? j : 0];
+        const uint2 qj = sh_q[have ? j : 0];
+        for (int w = 0; w <= jw; ++w) {
             unsigned word = 0u;
-            const int lim = min(32, j - 32 * w);
-            for (int ii = 0; ii < lim; ++ii) {
-                const int i = 32 * w + ii;
-                const bool sup = POS ? suppresses_pos(bj, aj, sh_box[i], sh_area[i], thr) : suppresses_any(bj, aj, sh_box[i], sh_area[i], thr);
-                word |= sup ? (1u << ii) : 0u;
+            const unsigned lim_mask = (w < jw) ? 0xFFFFFFFFu : ((1u << (j & 31)) - 1u);      // diagonal block: only i < j
+            if (POS) {
+                // branch-free integer prefilter over the 32 boxes of the block, then the exact test on the few survivors
+                unsigned cand = 0u;
+#pragma unroll
+                for (int ii = 0; ii < 32; ++ii) cand |= may_overlap(qj, sh_q[32 * w + ii]) ? (1u << ii) : 0u;
+                cand &= lim_mask;
+                while (cand) {
+                    const int ii = __ffs(cand) - 1;
+                    cand &= cand - 1;
+                    const int i = 32 * w + ii;
+                    if (suppresses_pos(bj, aj, sh_box[i], sh_area[i], thr)) word |= 1u << ii;
+                }
+            } else {
+#pragma unroll 4
+                for (int ii = 0; ii < 32; ++ii) {
+                    const int i = 32 * w + ii;
+                    if (((lim_mask >> ii) & 1u) && suppresses_any(bj, aj, sh_box[i], sh_area[i], thr)) word |= 1u << ii;
+                }
             }
-            sh_T[j][w] = word;
+            if (have) sh_T[j][w] = word;
         }
     }
 }
@@ -218,10 +282,11 @@ k_segment_nms_small(uint4 *__restrict__ cand, const unsigned *__restrict__ seg_c
                     const float4 *__restrict__ boxtab, long M, int C, int cap_seg, float thr, int seg_first,
                     unsigned *__restrict__ big_count, unsigned *__restrict__ big_list)
 {
-    __shared__ unsigned long long sh_key[SMALL_R];
+    __shared__ __align__(16) unsigned long long sh_key[SMALL_R + 2];
     __shared__ unsigned sh_row[SMALL_R], sh_conf[SMALL_R];      // sorted
     __shared__ float4 sh_box[SMALL_R];
     __shared__ float sh_area[SMALL_R];
+    __shared__ uint2 sh_q[SMALL_R];                             // 16-bit conservative corners for the pair prefilter
     __shared__ unsigned sh_T[SMALL_R][SMALL_W + 1];             // +1: conflict-free row writes
     __shared__ unsigned sh_kw[SMALL_W], sh_pref[SMALL_W + 1];
 
@@ -260,37 +325,42 @@ k_segment_nms_small(uint4 *__restrict__ cand, const unsigned *__restrict__ seg_c
         if (tid + u * SMALL_THREADS < n) bx[u] = boxes[row[u]];
     __syncthreads();
     int rank[2] = {0, 0};
-    for (int j = 0; j < n; ++j) {
-        const unsigned long long k = sh_key[j];
-        rank[0] += (k < key[0]) ? 1 : 0;
-        rank[1] += (k < key[1]) ? 1 : 0;
-    }
+    const int wbase = tid & ~31;                                // first element index of this warp (warp-uniform bounds below)
+    // keys beyond n were never written: pad the tail of the last 16-byte pair so the 2-wide loop may read it
+    if (tid == 0 && (n & 1)) sh_key[n] = ~0ull;
+    __syncthreads();
+    if (wbase < n) rank[0] = rank_of(sh_key, n, key[0]);
+    if (wbase + SMALL_THREADS < n) rank[1] = rank_of(sh_key, n, key[1]);
 #pragma unroll
     for (int u = 0; u < 2; ++u)
         if (tid + u * SMALL_THREADS < n) {
             const int r = rank[u];
             sh_row[r] = row[u]; sh_conf[r] = conf[u];
             sh_area[r] = box_area(bx[u]);
-            sh_box[r] = pos ? sanitise(bx[u]) : bx[u];
+            const float4 sb = pos ? sanitise(bx[u]) : bx[u];
+            sh_box[r] = sb;
+            sh_q[r] = quantise_box(sb);
         }
     __syncthreads();
-    if (pos) small_pairs<true>(sh_box, sh_area, sh_T, n, thr);
-    else small_pairs<false>(sh_box, sh_area, sh_T, n, thr);
+    if (pos) small_pairs<true>(sh_box, sh_area, sh_q, sh_T, n, thr);
+    else small_pairs<false>(sh_box, sh_area, sh_q, sh_T, n, thr);
     __syncthreads();
     if (tid < 32) {
         unsigned keptw = 0u;                                    // lane w owns kept word w
         const int lw = tid < SMALL_W ? tid : 0;
         int j = 0;
+        // row j only has words 0..j/32 (the rest was never written): lanes above the diagonal contribute nothing
         for (; j + 4 <= n; j += 4) {
-            unsigned t0 = sh_T[j][lw], t1 = sh_T[j + 1][lw], t2 = sh_T[j + 2][lw], t3 = sh_T[j + 3][lw];
-            if (tid >= SMALL_W) { t0 = t1 = t2 = t3 = 0u; }
+            const bool rd = tid <= (j >> 5);                    // j..j+3 share j>>5 (j is a multiple of 4)
+            const unsigned t0 = rd ? sh_T[j][lw] : 0u, t1 = rd ? sh_T[j + 1][lw] : 0u;
+            const unsigned t2 = rd ? sh_T[j + 2][lw] : 0u, t3 = rd ? sh_T[j + 3][lw] : 0u;
             if (!__any_sync(0xFFFFFFFFu, t0 & keptw) && tid == (j >> 5)) keptw |= 1u << (j & 31);
-            if (!__any_sync(0xFFFFFFFFu, t1 & keptw) && tid == ((j + 1) >> 5)) keptw |= 1u << ((j + 1) & 31);
-            if (!__any_sync(0xFFFFFFFFu, t2 & keptw) && tid == ((j + 2) >> 5)) keptw |= 1u << ((j + 2) & 31);
-            if (!__any_sync(0xFFFFFFFFu, t3 & keptw) && tid == ((j + 3) >> 5)) keptw |= 1u << ((j + 3) & 31);
+            if (!__any_sync(0xFFFFFFFFu, t1 & keptw) && tid == (j >> 5)) keptw |= 1u << ((j + 1) & 31);
+            if (!__any_sync(0xFFFFFFFFu, t2 & keptw) && tid == (j >> 5)) keptw |= 1u << ((j + 2) & 31);
+            if (!__any_sync(0xFFFFFFFFu, t3 & keptw) && tid == (j >> 5)) keptw |= 1u << ((j + 3) & 31);
         }
         for (; j < n; ++j) {
-            const unsigned t0 = (tid < SMALL_W) ? sh_T[j][lw] : 0u;
+            const unsigned t0 = (tid <= (j >> 5)) ? sh_T[j][lw] : 0u;
             if (!__any_sync(0xFFFFFFFFu, t0 & keptw) && tid == (j >> 5)) keptw |= 1u << (j & 31);
         }
         int c = (tid < SMALL_W) ? __popc(keptw) : 0, incl = c;
@@ -310,6 +380,168 @@ k_segment_nms_small(uint4 *__restrict__ cand, const unsigned *__restrict__ seg_c
             rec[q] = make_uint4(sh_row[j2], sh_conf[j2], 0u, 0u);        // {box row, cls_conf bits}
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Small tier, warp-per-segment form (default): one warp owns one (image,class) segment end to end, so there are no
+// block barriers and no warp ever idles while another resolves; a CTA is just WS_WARPS independent segments.
+//   1. records -> shared memory (key, row, conf) + box gather; 2. rank sort on the unique key;
+//   3. sorted conservative corners q[] + permutation;  4. per block of 32 sorted candidates: integer prefilter against
+//   every kept earlier box (exact fp32 test only on prefilter hits), 32x32 diagonal block, serial resolve by ballot,
+//   kept records appended in score order.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int WS_WARPS = 4;
+constexpr int WS_U = SMALL_R / 32;         // records per lane, at most
+
+struct alignas(16) WsSeg {
+    union {
+        unsigned long long key[SMALL_R + 2];   // while ranking
+        uint2 q[SMALL_R];                      // afterwards: conservative 16-bit corners in sorted order
+    };
+    float4 ubox[SMALL_R];                      // record order; sanitised when thr > 0
+    unsigned urow[SMALL_R], uconf[SMALL_R];    // record order
+    unsigned short perm[SMALL_R];              // sorted position -> record index
+};
+
+template <bool POS>
+__device__ __forceinline__ void warp_segment_nms(WsSeg &S, uint4 *__restrict__ rec, const float4 *__restrict__ boxes, int n,
+                                                 float thr, unsigned *kept_count_out)
+{
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31;
+    const int nu = (n + 31) >> 5;
+    unsigned long long mykey[WS_U];
+    // 1. records, then boxes (all loads of a phase in flight together)
+    {
+        uint4 r[WS_U];
+#pragma unroll
+        for (int u = 0; u < WS_U; ++u)
+            if (u < nu) { const int e = lane + 32 * u; r[u] = (e < n) ? rec[e] : make_uint4(0u, 0u, 0u, 0u); }
+        float4 bx[WS_U];
+#pragma unroll
+        for (int u = 0; u < WS_U; ++u)
+            if (u < nu) { const int e = lane + 32 * u; if (e < n) bx[u] = boxes[r[u].y]; }
+#pragma unroll
+        for (int u = 0; u < WS_U; ++u) {
+            mykey[u] = ~0ull;
+            if (u < nu) {
+                const int e = lane + 32 * u;
+                if (e < n) {
+                    mykey[u] = ((unsigned long long)score_desc_bits(r[u].x) << 32) | (unsigned)(~r[u].y);
+                    S.key[e] = mykey[u];
+                    S.urow[e] = r[u].y; S.uconf[e] = r[u].z;
+                    S.ubox[e] = POS ? sanitise(bx[u]) : bx[u];
+                }
+            }
+        }
+        if (lane == 0 && (n & 1)) S.key[n] = ~0ull;              // rank_of reads keys two at a time
+    }
+    __syncwarp();
+    // 2. rank
+    int rank[WS_U];
+#pragma unroll
+    for (int u = 0; u < WS_U; ++u) rank[u] = (u < nu) ? rank_of(S.key, n, mykey[u]) : 0;
+    __syncwarp();                                                // key storage is reused below
+    // 3. sorted prefilter corners + permutation
+#pragma unroll
+    for (int u = 0; u < WS_U; ++u)
+        if (u < nu) {
+            const int e = lane + 32 * u;
+            if (e < n) { S.q[rank[u]] = quantise_box(S.ubox[e]); S.perm[rank[u]] = (unsigned short)e; }
+        }
+    __syncwarp();
+    // 4. blocks of 32 in score order
+    unsigned keptw = 0u;                                         // lane w owns the kept bits of block w
+    int nk = 0;
+    for (int jb = 0; jb < nu; ++jb) {
+        const int j = 32 * jb + lane;
+        const bool have = j < n;
+        const int ej = have ? (int)S.perm[j] : 0;
+        const uint2 qj = have ? S.q[j] : make_uint2(0x7FFF7FFFu, 0u);
+        const float4 bj = S.ubox[ej];
+        const float aj = box_area(bj);
+        bool supp = false;
+        for (int ib = 0; ib < jb; ++ib) {
+            const unsigned kw = __shfl_sync(FULL, keptw, ib);
+            if (kw == 0u) continue;                              // warp-uniform
+            unsigned cand;
+            if (POS) {
+                cand = 0u;
+#pragma unroll
+                for (int ii = 0; ii < 32; ++ii) cand |= may_overlap(qj, S.q[32 * ib + ii]) ? (1u << ii) : 0u;
+                cand &= kw;
+            } else {
+                cand = kw;
+            }
+            if (!have || supp) cand = 0u;
+            while (cand) {
+                const int ii = __ffs(cand) - 1;
+                cand &= cand - 1;
+                const float4 bi = S.ubox[S.perm[32 * ib + ii]];
+                const bool sup = POS ? suppresses_pos(bj, aj, bi, box_area(bi), thr) : suppresses_any(bj, aj, bi, box_area(bi), thr);
+                if (sup) { supp = true; cand = 0u; }
+            }
+        }
+        // diagonal block: candidates i < j of the same block
+        const int nvalid = min(32, n - 32 * jb);
+        unsigned cand;
+        if (POS) {
+            cand = 0u;
+#pragma unroll
+            for (int ii = 0; ii < 32; ++ii) cand |= may_overlap(qj, S.q[32 * jb + ii]) ? (1u << ii) : 0u;
+        } else {
+            cand = FULL;
+        }
+        cand &= ((1u << lane) - 1u) & (nvalid == 32 ? FULL : ((1u << nvalid) - 1u));
+        if (!have || supp) cand = 0u;
+        unsigned word = 0u;
+        while (cand) {
+            const int ii = __ffs(cand) - 1;
+            cand &= cand - 1;
+            const float4 bi = S.ubox[S.perm[32 * jb + ii]];
+            const bool sup = POS ? suppresses_pos(bj, aj, bi, box_area(bi), thr) : suppresses_any(bj, aj, bi, box_area(bi), thr);
+            word |= sup ? (1u << ii) : 0u;
+        }
+        unsigned removed = __ballot_sync(FULL, supp || !have);
+        unsigned keep;
+        if (!__any_sync(FULL, word != 0u)) {
+            keep = ~removed;                                     // nothing inside the block suppresses anything
+        } else {
+            keep = 0u;
+            for (int i = 0; i < nvalid; ++i) {                   // warp-uniform serial resolve (utils.py:67-84)
+                const unsigned hit = __ballot_sync(FULL, (word >> i) & 1u);   // lanes that box i suppresses
+                if (!((removed >> i) & 1u)) { keep |= 1u << i; removed |= hit; }
+            }
+        }
+        if (lane == jb) keptw = keep;
+        if ((keep >> lane) & 1u) rec[nk + __popc(keep & ((1u << lane) - 1u))] = make_uint4(S.urow[ej], S.uconf[ej], 0u, 0u);
+        nk += __popc(keep);
+    }
+    if (lane == 0) *kept_count_out = (unsigned)nk;
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(WS_WARPS * 32)
+k_segment_nms_warp(uint4 *__restrict__ cand, const unsigned *__restrict__ seg_count, unsigned *__restrict__ kept_count,
+                   const float4 *__restrict__ boxtab, long M, int C, int cap_seg, float thr, int seg_first, int nseg,
+                   unsigned *__restrict__ big_count, unsigned *__restrict__ big_list)
+{
+    __shared__ WsSeg sh[WS_WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sl = blockIdx.x * WS_WARPS + warp;
+    if (sl >= nseg) return;
+    const int seg = seg_first + sl;
+    const unsigned cnt = seg_count[seg];
+    if (cnt == 0u) return;                                      // kept_count was zeroed by yl_post_reset
+    if (cnt > (unsigned)cap_seg) return;                        // overflow: reported through meta[], caller re-runs
+    if (cnt > (unsigned)SMALL_R) {
+        if (lane == 0) big_list[atomicAdd(big_count, 1u)] = (unsigned)seg;
+        return;
+    }
+    uint4 *rec = cand + (size_t)seg * cap_seg;
+    const float4 *boxes = boxtab + (size_t)(seg / C) * M;
+    if (thr > 0.0f) warp_segment_nms<true>(sh[warp], rec, boxes, (int)cnt, thr, &kept_count[seg]);
+    else warp_segment_nms<false>(sh[warp], rec, boxes, (int)cnt, thr, &kept_count[seg]);
 }
 
 // Big tier: persistent CTAs walk the list of segments the small tier could not take (more than SMALL_R candidates).
@@ -458,8 +690,13 @@ extern "C" int yl_nms(void *ws, size_t ws_bytes, int B, long M, int C, int cap_s
     const int nseg = img_count * C, seg_first = img_first * C;
     unsigned *big_count = (unsigned *)(w + L.off_big_count) + img_first;
     unsigned *big_list = (unsigned *)(w + L.off_big_list) + seg_first;
-    k_segment_nms_small<<<nseg, SMALL_THREADS, 0, (cudaStream_t)stream>>>(cand, seg_count, kept_count, boxtab, M, C, cap_seg,
-                                                                        nms_thre, seg_first, big_count, big_list);
+    static const bool cta_tier = getenv("YL_NMS_CTA") && getenv("YL_NMS_CTA")[0] == '1';     // A/B: block-per-segment form
+    if (cta_tier)
+        k_segment_nms_small<<<nseg, SMALL_THREADS, 0, (cudaStream_t)stream>>>(cand, seg_count, kept_count, boxtab, M, C, cap_seg,
+                                                                            nms_thre, seg_first, big_count, big_list);
+    else
+        k_segment_nms_warp<<<(nseg + WS_WARPS - 1) / WS_WARPS, WS_WARPS * 32, 0, (cudaStream_t)stream>>>(
+            cand, seg_count, kept_count, boxtab, M, C, cap_seg, nms_thre, seg_first, nseg, big_count, big_list);
     YL_LAUNCH_CHECK();
     if (cap_seg > SMALL_R) {
         const int grid_big = nseg < 148 * 2 ? nseg : 148 * 2;
