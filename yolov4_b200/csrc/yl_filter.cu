@@ -44,6 +44,8 @@ struct RawLayer {
     int row_off;           // rows of the lower scales in the concatenated [M] axis (yolov4.py:324)
     int tiles;             // CTAs along x for this scale
     int vec;               // 4 = 128-bit loads, 1 = scalar loads (planes not 16-byte aligned, e.g. 19x19)
+    int tma;               // streamed with TMA by k_filter_raw_tma (else register-staged loads)
+    int tile_boxes;        // boxes per warp tile in k_filter_raw_tma (128 TMA, 32 scalar)
     float stride;
     float aw[3], ah[3];    // masked anchors in grid units (yololayer.py:73-76)
 };
@@ -56,6 +58,9 @@ struct RawParams {
     unsigned *seg_count;
     float4 *boxtab;
     float *objtab;
+    unsigned *flags;       // split filter: [NW][B*M4] flag words (see PostLayout)
+    long M4;               // row pitch of flags / objtab in split mode (M rounded up to 4)
+    long BM4;              // B * M4
 };
 
 constexpr int K1_WARPS = K1_THREADS / 32;
@@ -139,7 +144,7 @@ __device__ __forceinline__ void emit_batch(const RawParams &P, const RawLayer &L
             const int lcs = (j == 0) ? lc[0] : ((j == 1) ? lc[1] : ((j == 2) ? lc[2] : lc[3]));
             const int bs = 32 * j + (int)__fns(wsel, 0, i - lcs + 1);
             const int p = wp0 + bs;
-            const size_t brow = (size_t)b * P.M + (row_base + p);
+            const size_t brow = (size_t)b * P.M4 + (row_base + p);
             P.boxtab[brow] = decode_box(wbase + bs, F2, Ly.Fw, p, Ly.aw[a], Ly.ah[a], Ly.stride);
             P.objtab[brow] = sobj[bs];
         }
@@ -217,45 +222,49 @@ struct LdgSmem {
     float sobj[K1_WARPS][128];
 };
 
+// Register-staged phase 1 for one lane: VEC consecutive boxes starting at p0 of (image, anchor) ba.
 template <int VEC, int NW>
-__device__ __forceinline__ void filter_tile(const RawParams &P, const RawLayer &Ly, int tile, int ba, LdgSmem &sm)
+__device__ __forceinline__ void ldg_stream(const RawParams &P, const RawLayer &Ly, int ba, int p0, bool inb,
+                                           float (&obj)[VEC], float (&lth)[VEC], unsigned (&bits)[VEC][NW])
 {
     const int C = P.C, F2 = Ly.F2;
     const float thr = P.thr;
-    const int p0 = (tile * K1_THREADS + threadIdx.x) * VEC;
-    const bool inb = p0 < F2;                                        // F2 % VEC == 0, so a vector is all in or all out
     const int nch = 5 + C;
     const float *base = Ly.raw + ((size_t)ba * nch) * F2 + (inb ? p0 : 0);
     const float *cp = base + 5 * (size_t)F2;
-
-    float obj[VEC], lth[VEC];
-    bool any_alive = false;
+    // The objectness plane and the first eight class planes are requested together: the bound needs sigmoid(obj),
+    // but the class loads do not, so no load latency is spent with nothing else in flight.
+    Vec<VEC> tob, t0[8];
+    const int kn0 = min(8, C);
     if (inb) {
-        Vec<VEC> tob;
         tob.load(base + 4 * (size_t)F2);
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-            obj[v] = spec_sigmoidf(tob.v[v]);
-            lth[v] = class_logit_bound(obj[v], thr);
-            any_alive |= (lth[v] != kInf);
-        }
-    } else {
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) { obj[v] = 0.0f; lth[v] = kInf; }
+        for (int u = 0; u < 8; ++u)
+            if (u < kn0) t0[u].load(cp + (size_t)u * F2);
     }
-
-    // ---- phase 1: streaming pass, result bits kept in registers -------------------------------------------------
-    unsigned bits[VEC][NW];
+    bool any_alive = false;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+        obj[v] = inb ? spec_sigmoidf(tob.v[v]) : 0.0f;
+        lth[v] = inb ? class_logit_bound(obj[v], thr) : kInf;
+        any_alive |= (lth[v] != kInf);
+    }
 #pragma unroll
     for (int v = 0; v < VEC; ++v)
 #pragma unroll
         for (int w = 0; w < NW; ++w) bits[v][w] = 0u;
     if (any_alive) {
 #pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (u < kn0) {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) flag_or(bits[v][0], t0[u].v[v], lth[v], 1u << u);
+            }
+#pragma unroll
         for (int w = 0; w < NW; ++w) {
             const int kn = min(32, C - 32 * w);
 #pragma unroll
-            for (int kk = 0; kk < 32; kk += 8) {                     // fully unrolled: every bit mask is an immediate
+            for (int kk = (w == 0 ? 8 : 0); kk < 32; kk += 8) {      // fully unrolled: every bit mask is an immediate
                 if (kk < kn) {
                     Vec<VEC> t[8];
 #pragma unroll
@@ -271,12 +280,122 @@ __device__ __forceinline__ void filter_tile(const RawParams &P, const RawLayer &
             }
         }
     }
+#pragma unroll
+    for (int v = 0; v < VEC; ++v)
+        if (lth[v] == kInf) {
+#pragma unroll
+            for (int w = 0; w < NW; ++w) bits[v][w] = 0u;
+        }
+}
+
+template <int VEC, int NW>
+__device__ __forceinline__ void filter_tile(const RawParams &P, const RawLayer &Ly, int tile, int ba, LdgSmem &sm)
+{
+    const int p0 = (tile * K1_THREADS + threadIdx.x) * VEC;
+    const bool inb = p0 < Ly.F2;                                     // F2 % VEC == 0, so a vector is all in or all out
+    float obj[VEC], lth[VEC];
+    unsigned bits[VEC][NW];
+    ldg_stream<VEC, NW>(P, Ly, ba, p0, inb, obj, lth, bits);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int v = 0; v < VEC; ++v) sm.sobj[warp][lane * VEC + v] = obj[v];
     emit_pairs<VEC, NW>(P, Ly, ba, (tile * K1_THREADS + warp * 32) * VEC, lth, bits, sm.e[warp], sm.sobj[warp]);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Split form (default): the streaming kernel does nothing but load, compare and store 16 bytes per box (flag words +
+// sigmoid(objectness)), so it runs at the memory system's pace; k_emit_flagged then resolves the flagged pairs.
+// ---------------------------------------------------------------------------------------------------------------
+template <int VEC, int NW>
+__device__ __forceinline__ void flag_tile(const RawParams &P, const RawLayer &Ly, int tile, int ba)
+{
+    const int p0 = (tile * K1_THREADS + threadIdx.x) * VEC;
+    if (p0 >= Ly.F2) return;                                         // F2 % VEC == 0: a vector is all in or all out
+    float obj[VEC], lth[VEC];
+    unsigned bits[VEC][NW];
+    ldg_stream<VEC, NW>(P, Ly, ba, p0, true, obj, lth, bits);
+    const int b = ba / 3, a = ba - 3 * b;
+    const size_t r = (size_t)b * P.M4 + (Ly.row_off + a * Ly.F2 + p0);
+    if (VEC == 4) {
+        *reinterpret_cast<float4 *>(P.objtab + r) = make_float4(obj[0], obj[1], obj[2], obj[3]);
+#pragma unroll
+        for (int w = 0; w < NW; ++w)
+            *reinterpret_cast<uint4 *>(P.flags + (size_t)w * P.BM4 + r) = make_uint4(bits[0][w], bits[1][w], bits[2][w], bits[3][w]);
+    } else {
+        P.objtab[r] = obj[0];
+#pragma unroll
+        for (int w = 0; w < NW; ++w) P.flags[(size_t)w * P.BM4 + r] = bits[0][w];
+    }
+}
+
+#ifndef YL_FLAG_MINB
+#define YL_FLAG_MINB 8
+#endif
+template <int NW>
+__global__ void __launch_bounds__(K1_THREADS, YL_FLAG_MINB)
+k_flag_raw(const __grid_constant__ RawParams P)
+{
+    const int ba = P.img_first * 3 + blockIdx.y;
+    int tile = blockIdx.x;
+    int l = 0;
+    while (l < P.n_layers - 1 && tile >= P.layer[l].tiles) { tile -= P.layer[l].tiles; ++l; }
+    if (P.layer[l].vec == 4) flag_tile<4, NW>(P, P.layer[l], tile, ba);
+    else flag_tile<1, NW>(P, P.layer[l], tile, ba);
+}
+
+template <int VEC, int NW>
+__device__ __forceinline__ void emit_tile(const RawParams &P, const RawLayer &Ly, int tile, int ba, LdgSmem &sm)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int p0 = (tile * K1_THREADS + threadIdx.x) * VEC;
+    const bool inb = p0 < Ly.F2;
+    const int b = ba / 3, a = ba - 3 * b;
+    const size_t r = (size_t)b * P.M4 + (Ly.row_off + a * Ly.F2 + (inb ? p0 : 0));
+    float lth[VEC];
+    unsigned bits[VEC][NW];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) lth[v] = 0.0f;
+    if (VEC == 4) {
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            const uint4 m = inb ? *reinterpret_cast<const uint4 *>(P.flags + (size_t)w * P.BM4 + r) : make_uint4(0u, 0u, 0u, 0u);
+            bits[0][w] = m.x; bits[1 % VEC][w] = m.y; bits[2 % VEC][w] = m.z; bits[3 % VEC][w] = m.w;
+        }
+    } else {
+#pragma unroll
+        for (int w = 0; w < NW; ++w) bits[0][w] = inb ? P.flags[(size_t)w * P.BM4 + r] : 0u;
+    }
+    unsigned any = 0u;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v)
+#pragma unroll
+        for (int w = 0; w < NW; ++w) any |= bits[v][w];
+    if (!__any_sync(0xFFFFFFFFu, any != 0u)) return;                 // warp-uniform: nothing flagged in these 32*VEC boxes
+    if (VEC == 4) {
+        const float4 o = inb ? *reinterpret_cast<const float4 *>(P.objtab + r) : make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4 *>(&sm.sobj[warp][lane * 4]) = o;
+    } else {
+        sm.sobj[warp][lane] = inb ? P.objtab[r] : 0.0f;
+    }
+    emit_pairs<VEC, NW>(P, Ly, ba, (tile * K1_THREADS + warp * 32) * VEC, lth, bits, sm.e[warp], sm.sobj[warp]);
+}
+
+#ifndef YL_EMIT_MINB
+#define YL_EMIT_MINB 10
+#endif
+template <int NW>
+__global__ void __launch_bounds__(K1_THREADS, YL_EMIT_MINB)
+k_emit_flagged(const __grid_constant__ RawParams P)
+{
+    __shared__ LdgSmem sm;
+    const int ba = P.img_first * 3 + blockIdx.y;
+    int tile = blockIdx.x;
+    int l = 0;
+    while (l < P.n_layers - 1 && tile >= P.layer[l].tiles) { tile -= P.layer[l].tiles; ++l; }
+    if (P.layer[l].vec == 4) emit_tile<4, NW>(P, P.layer[l], tile, ba, sm);
+    else emit_tile<1, NW>(P, P.layer[l], tile, ba, sm);
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // TMA form of the streaming pass (scales whose planes are 16-byte aligned: 76/38 @608, 52/26 @416).
@@ -304,6 +423,7 @@ struct alignas(128) WtWarp {
     float stage[WT_STAGES][WT_KC][WT_BOX];     // 12 KB
     float objp[2][WT_BOX];                     // objectness plane of the current / the next tile
     unsigned long long full[WT_STAGES], obj_full[2];
+    float sobj1[32];                           // sigmoid(objectness) of a scalar (non-TMA) warp tile
     EmitWarp em;
 };
 struct WtSmem {
@@ -347,22 +467,39 @@ struct WtTile {
     const float *src;      // plane 0 of this (image, anchor) at the tile's first box
     int layer, ba, p0, np; // np = boxes in the tile (<= 128, multiple of 4); np == 0: no tile
     int row0;              // plane row of class 0 in the scale's 2-D view: ba*(5+C) + 5
+    int tma;
 };
 
 // P.layer[] holds only the TMA-capable scales; layer[l].tiles = ceil(F2 / WT_BOX) warp tiles per (image, anchor).
+// Tile queue order: TMA tiles with the scalar tiles spread evenly among them (one scalar tile after every `every`
+// TMA tiles), so the latency-bound scalar tiles overlap the streaming ones instead of forming a tail.
 __device__ __forceinline__ WtTile wt_tile(const RawParams &P, int t, int n_tiles, int nba)
 {
     WtTile T;
-    T.np = 0; T.src = nullptr; T.layer = 0; T.ba = 0; T.p0 = 0; T.row0 = 0;
+    T.np = 0; T.src = nullptr; T.layer = 0; T.ba = 0; T.p0 = 0; T.row0 = 0; T.tma = 0;
     if (t >= n_tiles) return T;
+    int n_tma = 0;
+    for (int l = 0; l < P.n_layers; ++l) n_tma += P.layer[l].tma ? P.layer[l].tiles * nba : 0;
+    const int n_sc = n_tiles - n_tma;
+    if (n_sc > 0 && n_tma >= n_sc) {
+        // queue position -> tile index (TMA tiles are indices [0, n_tma), scalar tiles [n_tma, n_tiles))
+        const int every = n_tma / n_sc, G = every + 1;
+        if (t < n_sc * G) {
+            const int g = t / G, r = t - g * G;
+            t = (r < every) ? g * every + r : n_tma + g;
+        } else {
+            t = n_sc * every + (t - n_sc * G);                       // the n_tma % n_sc TMA tiles left over
+        }
+    }
     int l = 0;
     while (l < P.n_layers - 1 && t >= P.layer[l].tiles * nba) { t -= P.layer[l].tiles * nba; ++l; }
     const int tp = P.layer[l].tiles;
     const int bal = t / tp, tx = t - bal * tp;
     T.layer = l;
     T.ba = P.img_first * 3 + bal;
-    T.p0 = tx * WT_BOX;
-    T.np = min(WT_BOX, P.layer[l].F2 - T.p0);
+    T.p0 = tx * P.layer[l].tile_boxes;
+    T.np = min(P.layer[l].tile_boxes, P.layer[l].F2 - T.p0);
+    T.tma = P.layer[l].tma;
     T.src = P.layer[l].raw + ((size_t)T.ba * (5 + P.C)) * P.layer[l].F2 + T.p0;
     T.row0 = T.ba * (5 + P.C) + 5;
     return T;
@@ -407,7 +544,7 @@ k_filter_raw_tma(const __grid_constant__ RawParams P, const __grid_constant__ Tm
 
     WtTile cur = fetch_tile();
     if (cur.np == 0) return;
-    if (lane == 0) {
+    if (lane == 0 && cur.tma) {
         issue_obj(cur, 0);
         for (int c = 0; c < WT_STAGES && c < n_cc; ++c) issue_chunk(cur, c, c);
     }
@@ -416,9 +553,25 @@ k_filter_raw_tma(const __grid_constant__ RawParams P, const __grid_constant__ Tm
     unsigned it = 0u;                // tiles processed by this warp (objectness slot = it & 1, phase = (it >> 1) & 1)
 
     while (cur.np != 0) {
-        const WtTile nxt = fetch_tile();
-        if (lane == 0 && nxt.np != 0) issue_obj(nxt, (it + 1) & 1);
+        WtTile nxt = fetch_tile();
         const RawLayer &Ly = P.layer[cur.layer];
+        if (!cur.tma) {
+            // scalar tile (planes not 16-byte aligned, e.g. the 19x19 scale): register-staged loads, 32 boxes per warp
+            float obj1[1], lth1[1];
+            unsigned bits1[1][NW];
+            // a TMA tile may follow: start its objectness plane and first chunks now, they land while this tile runs
+            if (lane == 0 && nxt.np != 0 && nxt.tma) {
+                issue_obj(nxt, it & 1);
+                for (int c = 0; c < WT_STAGES && c < n_cc; ++c) issue_chunk(nxt, c, (s + c) % WT_STAGES);
+            }
+            ldg_stream<1, NW>(P, Ly, cur.ba, cur.p0 + lane, lane < cur.np, obj1, lth1, bits1);
+            W.sobj1[lane] = obj1[0];
+            emit_pairs<1, NW>(P, Ly, cur.ba, cur.p0, lth1, bits1, W.em, W.sobj1);
+            cur = nxt;
+            continue;
+        }
+        if (!nxt.tma) nxt.np = -nxt.np;                          // no prefetch into a scalar tile (restored below)
+        if (lane == 0 && nxt.np > 0) issue_obj(nxt, (it + 1) & 1);
         const bool inb = lane * 4 < cur.np;
         float obj[4], lth[4];
         {
@@ -458,7 +611,7 @@ k_filter_raw_tma(const __grid_constant__ RawParams P, const __grid_constant__ Tm
                 if (lane == 0) {
                     const int cn = c + WT_STAGES;                    // the chunk that takes this stage next
                     if (cn < n_cc) issue_chunk(cur, cn, s);
-                    else if (nxt.np != 0 && cn - n_cc < n_cc) issue_chunk(nxt, cn - n_cc, s);
+                    else if (nxt.np > 0 && cn - n_cc < n_cc) issue_chunk(nxt, cn - n_cc, s);
                 }
                 ph ^= 1u << s;
                 s = (s + 1 == WT_STAGES) ? 0 : s + 1;
@@ -468,6 +621,7 @@ k_filter_raw_tma(const __grid_constant__ RawParams P, const __grid_constant__ Tm
         // sigmoid(objectness) replaces the logits in the tile's objectness slot: the exact pass reads it per box slot
         *reinterpret_cast<float4 *>(&W.objp[it & 1][lane * 4]) = make_float4(obj[0], obj[1], obj[2], obj[3]);
         emit_pairs<4, NW>(P, Ly, cur.ba, cur.p0, lth, bits, W.em, W.objp[it & 1]);
+        if (nxt.np < 0) nxt.np = -nxt.np;
         cur = nxt;
         ++it;
     }
@@ -492,7 +646,7 @@ constexpr int KD_THREADS = 256;
 constexpr int KD_MAXJ = (5 + YL_MAX_CLASSES + 31) / 32;
 
 __global__ void __launch_bounds__(KD_THREADS)
-k_filter_dense(const float *__restrict__ pred, long M, int C, int num_classes, float thr, int cap_seg,
+k_filter_dense(const float *__restrict__ pred, long M, long M4, int C, int num_classes, float thr, int cap_seg,
                int img_first, long n_rows,
                uint4 *__restrict__ cand, unsigned *__restrict__ seg_count,
                float4 *__restrict__ boxtab, float *__restrict__ objtab)
@@ -534,7 +688,7 @@ k_filter_dense(const float *__restrict__ pred, long M, int C, int num_classes, f
             any |= pass[j];
         }
         if (!__any_sync(0xFFFFFFFFu, any)) continue;
-        const size_t brow = (size_t)b * M + row;
+        const size_t brow = (size_t)b * M4 + row;
         const float cx = __shfl_sync(0xFFFFFFFFu, e[0], 0), cy = __shfl_sync(0xFFFFFFFFu, e[0], 1);
         const float w = __shfl_sync(0xFFFFFFFFu, e[0], 2), h = __shfl_sync(0xFFFFFFFFu, e[0], 3);
         if (lane == 0) {
@@ -565,6 +719,9 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32
 
 // YL_NO_TMA=1 forces the register-staged LDG kernel for every scale (A/B measurements).
 static const bool g_use_tma = !(getenv("YL_NO_TMA") && getenv("YL_NO_TMA")[0] == '1');
+// YL_FILTER selects the front-end form: "split" (default: lean streaming flag kernel + emit kernel),
+// "fused" (one kernel streams and emits: the TMA pipeline where planes are 16-byte aligned, register-staged otherwise).
+static const bool g_split = !(getenv("YL_FILTER") && strcmp(getenv("YL_FILTER"), "fused") == 0);
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda).
 static int encode_plane_map(CUtensorMap *map, const float *raw, int F2, long rows)
 {
@@ -629,10 +786,12 @@ extern "C" int yl_filter_raw(const float *const *raw, const int *F, int n_layers
     RawParams base;
     base.C = C; base.cap_seg = cap_seg; base.img_first = img_first; base.M = M; base.thr = conf_thre;
     base.cand = cand; base.seg_count = seg_count; base.boxtab = boxtab; base.objtab = objtab; base.n_layers = 0;
-    RawParams Pt = base, Pl = base;                                          // TMA-capable scales / the rest (LDG)
-    int row_off = 0, tiles_tma = 0, tiles_ldg = 0;
+    base.flags = (unsigned *)(w + L.off_flags); base.M4 = L.M4; base.BM4 = (long)B * L.M4;
+    RawParams Pt = base, Pl = base;                 // Pt: persistent TMA kernel (TMA scales first, scalar scales last); Pl: LDG kernel
+    RawLayer lay[3];
+    int row_off = 0, tiles_tma = 0, tiles_ldg = 0, n_tma = 0;
     for (int l = 0; l < n_layers; ++l) {
-        RawLayer Ly;
+        RawLayer &Ly = lay[l];
         Ly.raw = raw[l]; Ly.Fw = F[l]; Ly.F2 = F[l] * F[l]; Ly.row_off = row_off;
         Ly.stride = (float)(8 << l);                                        // yololayer.py:54
         for (int a = 0; a < 3; ++a) {                                       // yololayer.py:73-76 (doubles, then fp32)
@@ -643,17 +802,28 @@ extern "C" int yl_filter_raw(const float *const *raw, const int *F, int n_layers
         }
         // 128-bit loads / bulk copies need 16-byte aligned planes: F^2 % 4 == 0 and an aligned base (19x19, 13x13 fall back)
         Ly.vec = ((Ly.F2 % 4 == 0) && (((uintptr_t)raw[l]) % 16 == 0)) ? 4 : 1;
-        if (Ly.vec == 4 && g_use_tma && (C + WT_KC - 1) / WT_KC >= WT_STAGES) {
-            Ly.tiles = (Ly.F2 + WT_BOX - 1) / WT_BOX;
-            tiles_tma += Ly.tiles;
-            Pt.layer[Pt.n_layers++] = Ly;
-        } else {
-            Ly.tiles = (Ly.F2 / Ly.vec + K1_THREADS - 1) / K1_THREADS;
-            tiles_ldg += Ly.tiles;
-            Pl.layer[Pl.n_layers++] = Ly;
-        }
+        Ly.tma = (Ly.vec == 4 && g_use_tma && (C + WT_KC - 1) / WT_KC >= WT_STAGES) ? 1 : 0;
+        n_tma += Ly.tma;
         row_off += 3 * Ly.F2;
     }
+    if (g_split) n_tma = 0;
+    for (int pass = 0; pass < 2; ++pass)
+        for (int l = 0; l < n_layers; ++l) {
+            RawLayer Ly = lay[l];
+            if (n_tma > 0) {                                                 // everything goes through the persistent kernel
+                if ((pass == 0) != (Ly.tma == 1)) continue;
+                Ly.tile_boxes = Ly.tma ? WT_BOX : 32;
+                Ly.tiles = (Ly.F2 + Ly.tile_boxes - 1) / Ly.tile_boxes;
+                tiles_tma += Ly.tiles;
+                Pt.layer[Pt.n_layers++] = Ly;
+            } else if (pass == 0) {
+                Ly.tma = 0;
+                Ly.tile_boxes = K1_THREADS * Ly.vec;
+                Ly.tiles = (Ly.F2 / Ly.vec + K1_THREADS - 1) / K1_THREADS;
+                tiles_ldg += Ly.tiles;
+                Pl.layer[Pl.n_layers++] = Ly;
+            }
+        }
     for (int l = Pt.n_layers; l < 3; ++l) { Pt.layer[l] = Pt.layer[0]; Pt.layer[l].tiles = 0; }
     for (int l = Pl.n_layers; l < 3; ++l) { Pl.layer[l] = Pl.layer[0]; Pl.layer[l].tiles = 0; }
     cudaStream_t st = (cudaStream_t)stream;
@@ -670,6 +840,7 @@ extern "C" int yl_filter_raw(const float *const *raw, const int *F, int n_layers
         TmaMaps maps;
         memset(&maps, 0, sizeof(maps));
         for (int l = 0; l < Pt.n_layers; ++l) {
+            if (!Pt.layer[l].tma) continue;
             const int rc = encode_plane_map(&maps.m[l], Pt.layer[l].raw, Pt.layer[l].F2, (long)B * 3 * (5 + C));
             if (rc != YL_OK) return rc;
         }
@@ -688,11 +859,27 @@ extern "C" int yl_filter_raw(const float *const *raw, const int *F, int n_layers
     }
     if (Pl.n_layers > 0) {
         dim3 grid(tiles_ldg, img_count * 3);
-        switch (NW) {
-        case 1: k_filter_raw<1><<<grid, K1_THREADS, 0, st>>>(Pl); break;
-        case 2: k_filter_raw<2><<<grid, K1_THREADS, 0, st>>>(Pl); break;
-        case 3: k_filter_raw<3><<<grid, K1_THREADS, 0, st>>>(Pl); break;
-        default: k_filter_raw<4><<<grid, K1_THREADS, 0, st>>>(Pl); break;
+        if (g_split) {
+            switch (NW) {
+            case 1: k_flag_raw<1><<<grid, K1_THREADS, 0, st>>>(Pl); break;
+            case 2: k_flag_raw<2><<<grid, K1_THREADS, 0, st>>>(Pl); break;
+            case 3: k_flag_raw<3><<<grid, K1_THREADS, 0, st>>>(Pl); break;
+            default: k_flag_raw<4><<<grid, K1_THREADS, 0, st>>>(Pl); break;
+            }
+            YL_LAUNCH_CHECK();
+            switch (NW) {
+            case 1: k_emit_flagged<1><<<grid, K1_THREADS, 0, st>>>(Pl); break;
+            case 2: k_emit_flagged<2><<<grid, K1_THREADS, 0, st>>>(Pl); break;
+            case 3: k_emit_flagged<3><<<grid, K1_THREADS, 0, st>>>(Pl); break;
+            default: k_emit_flagged<4><<<grid, K1_THREADS, 0, st>>>(Pl); break;
+            }
+        } else {
+            switch (NW) {
+            case 1: k_filter_raw<1><<<grid, K1_THREADS, 0, st>>>(Pl); break;
+            case 2: k_filter_raw<2><<<grid, K1_THREADS, 0, st>>>(Pl); break;
+            case 3: k_filter_raw<3><<<grid, K1_THREADS, 0, st>>>(Pl); break;
+            default: k_filter_raw<4><<<grid, K1_THREADS, 0, st>>>(Pl); break;
+            }
         }
         YL_LAUNCH_CHECK();
     }
@@ -714,7 +901,7 @@ extern "C" int yl_filter_dense(const float *pred, int B, long M, int C, int num_
     const long blocks_needed = (n_rows * 32 + KD_THREADS - 1) / KD_THREADS;
     const int grid = (int)(blocks_needed < 148L * 64 ? blocks_needed : 148L * 64);
     k_filter_dense<<<grid, KD_THREADS, 0, (cudaStream_t)stream>>>(
-        pred, M, C, num_classes, conf_thre, cap_seg, img_first, n_rows, (uint4 *)(w + L.off_cand),
+        pred, M, L.M4, C, num_classes, conf_thre, cap_seg, img_first, n_rows, (uint4 *)(w + L.off_cand),
         (unsigned *)(w + L.off_seg_count), (float4 *)(w + L.off_box), (float *)(w + L.off_obj));
     YL_LAUNCH_CHECK();
     return YL_OK;

@@ -692,19 +692,19 @@ extern "C" int yl_nms(void *ws, size_t ws_bytes, int B, long M, int C, int cap_s
     unsigned *big_list = (unsigned *)(w + L.off_big_list) + seg_first;
     static const bool cta_tier = getenv("YL_NMS_CTA") && getenv("YL_NMS_CTA")[0] == '1';     // A/B: block-per-segment form
     if (cta_tier)
-        k_segment_nms_small<<<nseg, SMALL_THREADS, 0, (cudaStream_t)stream>>>(cand, seg_count, kept_count, boxtab, M, C, cap_seg,
+        k_segment_nms_small<<<nseg, SMALL_THREADS, 0, (cudaStream_t)stream>>>(cand, seg_count, kept_count, boxtab, L.M4, C, cap_seg,
                                                                             nms_thre, seg_first, big_count, big_list);
     else
         k_segment_nms_warp<<<(nseg + WS_WARPS - 1) / WS_WARPS, WS_WARPS * 32, 0, (cudaStream_t)stream>>>(
-            cand, seg_count, kept_count, boxtab, M, C, cap_seg, nms_thre, seg_first, nseg, big_count, big_list);
+            cand, seg_count, kept_count, boxtab, L.M4, C, cap_seg, nms_thre, seg_first, nseg, big_count, big_list);
     YL_LAUNCH_CHECK();
     if (cap_seg > SMALL_R) {
         const int grid_big = nseg < 148 * 2 ? nseg : 148 * 2;
-        k_segment_nms_big<<<grid_big, NMS_THREADS, 0, (cudaStream_t)stream>>>(cand, seg_count, kept_count, boxtab, M, C, cap_seg,
+        k_segment_nms_big<<<grid_big, NMS_THREADS, 0, (cudaStream_t)stream>>>(cand, seg_count, kept_count, boxtab, L.M4, C, cap_seg,
                                                                              nms_thre, big_count, big_list, kept_scratch);
         YL_LAUNCH_CHECK();
     }
-    k_gather_rows<<<nseg, GATHER_THREADS, 0, (cudaStream_t)stream>>>(cand, seg_count, kept_count, boxtab, objtab, M, C,
+    k_gather_rows<<<nseg, GATHER_THREADS, 0, (cudaStream_t)stream>>>(cand, seg_count, kept_count, boxtab, objtab, L.M4, C,
                                                                    cap_seg, B, out_rows, cap_out, meta, seg_first);
     YL_LAUNCH_CHECK();
     return YL_OK;
