@@ -27,6 +27,9 @@ IMG, C, CONF, NMS = 608, 80, 1e-4, 0.4
 GRIDS = [76, 38, 19]
 BYTES_PER_IMAGE = sum(3 * f * f for f in GRIDS) * (5 + C) * 4          # 7 732 620 B
 METRIC = "images/sec decode+NMS @608 b64 conf1e-4"
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_flag_raw<3> launch at B=64 from the ncu --set full capture in
+# profiles/
+TRAFFIC_PER_LAUNCH = 475977728 + 13604096   # profiles/r1_k_flag_raw_ncu_full_raw.csv
 UNIT = "images/s"
 
 
@@ -125,7 +128,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
-    ap.add_argument("--groups", type=int, default=4, help="image groups pipelined over two streams")
+    ap.add_argument("--groups", type=int, default=1, help="image groups pipelined over two streams")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--cpu-sample", type=int, default=32, help="images timed for the CPU baseline (0 = skip)")
     args = ap.parse_args()
@@ -180,17 +183,18 @@ def main():
     st = torch.cuda.current_stream().cuda_stream
     rp = _cabi.ptrs([r.data_ptr() for r in hp._captured_inputs])
 
-    def filter_stage():
-        _cabi.check(L.yl_post_reset(hp.ws.ptr(), hp.ws.nbytes, B, hp.M, C, hp.cap_seg, st))
-        _cabi.check(L.yl_filter_raw(rp, hp.fs, 3, B, C, hp.anch, hp.mask, hp.conf, hp.ws.ptr(), hp.ws.nbytes, hp.M, hp.cap_seg, 0, B, st))
+    def flag_kernel():
+        # the dominant kernel alone: k_flag_raw streams every raw byte once (one launch covers the three scales)
+        _cabi.check(L.yl_filter_raw_stage(rp, hp.fs, 3, B, C, hp.anch, hp.mask, hp.conf, hp.ws.ptr(), hp.ws.nbytes, hp.M,
+                                          hp.cap_seg, 0, B, 1, st))
 
     for _ in range(args.warmup):
-        filter_stage()
+        flag_kernel()
     torch.cuda.synchronize()
     n_f = max(20, min(args.steps, 200))
     ev0.record()
     for _ in range(n_f):
-        filter_stage()
+        flag_kernel()
     ev1.record()
     torch.cuda.synchronize()
     t_filter = ev0.elapsed_time(ev1) / 1e3 / n_f
@@ -242,13 +246,15 @@ def main():
             "config": {"workload": "yolov4 head outputs batch %d/GPU @608x608 (grids 76/38/19), 80 classes, conf 1e-4, nms 0.4 "
                                    "(BASELINE configs[1])" % B,
                        "l2": "inputs (495 MB/step) are larger than L2 (126 MB); no flush needed",
-                       "timed": "CUDA-graph replay of reset + %d x (3 filter launches | segment NMS + gather)" % hp.n_groups,
+                       "timed": "CUDA-graph replay of counter reset + flag + emit + segment NMS (warp tier, big tier) + gather",
                        "rows_per_step": rows_per_step, "parallelism": "images sharded by rank, no collective on the hot path"},
             "gpu_launches": hp.launches_per_run * args.steps,
             "e2e": e2e,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "k_filter_raw (decode+filter, one launch per scale, timed together)",
-                         "us_per_launch_set": t_filter * 1e6, "peak_source": peak_src,
+                         "traffic": TRAFFIC_PER_LAUNCH,
+                         "kernel": "k_flag_raw<3> (streaming decode+filter pass over the raw head tensors, one launch per step)",
+                         "us_per_launch": t_filter * 1e6, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": B * BYTES_PER_IMAGE,
                          "whole_step_frac": (B * BYTES_PER_IMAGE / (sec / args.steps) / 1e9) / peak},
             "cpu_baseline": cpu,
             "clocks": clocks,

@@ -97,6 +97,13 @@ int yl_filter_raw(const float *const *raw, const int *F, int n_layers, int B, in
                   void *ws, size_t ws_bytes, long M, int cap_seg, int img_first, int img_count,
                   yl_stream_t stream);
 
+/* The two kernels of yl_filter_raw run separately (measurement / pipelining): stages bit 0 = streaming flag kernel
+ * (reads every raw byte once, writes 16 B per box), bit 1 = emit kernel (resolves the flagged pairs exactly). */
+int yl_filter_raw_stage(const float *const *raw, const int *F, int n_layers, int B, int C,
+                        const float *anchors_px, const int *anchor_mask, float conf_thre,
+                        void *ws, size_t ws_bytes, long M, int cap_seg, int img_first, int img_count,
+                        int stages, yl_stream_t stream);
+
 /* pred [B, M, 5+C] decoded (cx,cy,w,h,obj,cls...), not modified (the reference's in-place xyxy overwrite,
  * utils.py:126, is an unobserved side effect).  num_classes <= C limits the row pre-filter (utils.py:139). */
 int yl_filter_dense(const float *pred, int B, long M, int C, int num_classes, float conf_thre,

@@ -46,6 +46,8 @@ def lib():
     L.yl_post_reset.argtypes = [_p, _sz, _i, _l, _i, _i, _p]
     L.yl_filter_raw.restype = _i
     L.yl_filter_raw.argtypes = [_p, _p, _i, _i, _i, _p, _p, _f, _p, _sz, _l, _i, _i, _i, _p]
+    L.yl_filter_raw_stage.restype = _i
+    L.yl_filter_raw_stage.argtypes = [_p, _p, _i, _i, _i, _p, _p, _f, _p, _sz, _l, _i, _i, _i, _i, _p]
     L.yl_filter_dense.restype = _i
     L.yl_filter_dense.argtypes = [_p, _i, _l, _i, _i, _f, _p, _sz, _i, _i, _i, _p]
     L.yl_nms.restype = _i
@@ -66,7 +68,7 @@ def lib():
 
 EXPORTS = [
     "yl_abi_version", "yl_error_string", "yl_decode_dense", "yl_decode_train", "yl_decode_train_backward",
-    "yl_post_workspace_bytes", "yl_post_reset", "yl_filter_raw", "yl_filter_dense", "yl_nms", "yl_build_target",
+    "yl_post_workspace_bytes", "yl_post_reset", "yl_filter_raw", "yl_filter_raw_stage", "yl_filter_dense", "yl_nms", "yl_build_target",
     "yl_context_create", "yl_context_destroy", "yl_detect_host",
 ]
 

@@ -763,10 +763,10 @@ extern "C" int yl_post_reset(void *ws, size_t ws_bytes, int B, long M, int C, in
     return YL_OK;
 }
 
-extern "C" int yl_filter_raw(const float *const *raw, const int *F, int n_layers, int B, int C,
-                             const float *anchors_px, const int *anchor_mask, float conf_thre,
-                             void *ws, size_t ws_bytes, long M, int cap_seg, int img_first, int img_count,
-                             yl_stream_t stream)
+static int filter_raw_impl(const float *const *raw, const int *F, int n_layers, int B, int C,
+                           const float *anchors_px, const int *anchor_mask, float conf_thre,
+                           void *ws, size_t ws_bytes, long M, int cap_seg, int img_first, int img_count,
+                           yl_stream_t stream, int stages)
 {
     if (!raw || !F || !anchors_px || !anchor_mask || !ws) return YL_ERR_ARG;
     if (n_layers < 1 || n_layers > 3 || B <= 0 || C <= 0 || cap_seg <= 0) return YL_ERR_ARG;
@@ -860,18 +860,22 @@ extern "C" int yl_filter_raw(const float *const *raw, const int *F, int n_layers
     if (Pl.n_layers > 0) {
         dim3 grid(tiles_ldg, img_count * 3);
         if (g_split) {
-            switch (NW) {
-            case 1: k_flag_raw<1><<<grid, K1_THREADS, 0, st>>>(Pl); break;
-            case 2: k_flag_raw<2><<<grid, K1_THREADS, 0, st>>>(Pl); break;
-            case 3: k_flag_raw<3><<<grid, K1_THREADS, 0, st>>>(Pl); break;
-            default: k_flag_raw<4><<<grid, K1_THREADS, 0, st>>>(Pl); break;
+            if (stages & 1) {
+                switch (NW) {
+                case 1: k_flag_raw<1><<<grid, K1_THREADS, 0, st>>>(Pl); break;
+                case 2: k_flag_raw<2><<<grid, K1_THREADS, 0, st>>>(Pl); break;
+                case 3: k_flag_raw<3><<<grid, K1_THREADS, 0, st>>>(Pl); break;
+                default: k_flag_raw<4><<<grid, K1_THREADS, 0, st>>>(Pl); break;
+                }
+                YL_LAUNCH_CHECK();
             }
-            YL_LAUNCH_CHECK();
-            switch (NW) {
-            case 1: k_emit_flagged<1><<<grid, K1_THREADS, 0, st>>>(Pl); break;
-            case 2: k_emit_flagged<2><<<grid, K1_THREADS, 0, st>>>(Pl); break;
-            case 3: k_emit_flagged<3><<<grid, K1_THREADS, 0, st>>>(Pl); break;
-            default: k_emit_flagged<4><<<grid, K1_THREADS, 0, st>>>(Pl); break;
+            if (stages & 2) {
+                switch (NW) {
+                case 1: k_emit_flagged<1><<<grid, K1_THREADS, 0, st>>>(Pl); break;
+                case 2: k_emit_flagged<2><<<grid, K1_THREADS, 0, st>>>(Pl); break;
+                case 3: k_emit_flagged<3><<<grid, K1_THREADS, 0, st>>>(Pl); break;
+                default: k_emit_flagged<4><<<grid, K1_THREADS, 0, st>>>(Pl); break;
+                }
             }
         } else {
             switch (NW) {
@@ -884,6 +888,25 @@ extern "C" int yl_filter_raw(const float *const *raw, const int *F, int n_layers
         YL_LAUNCH_CHECK();
     }
     return YL_OK;
+}
+
+extern "C" int yl_filter_raw(const float *const *raw, const int *F, int n_layers, int B, int C,
+                             const float *anchors_px, const int *anchor_mask, float conf_thre,
+                             void *ws, size_t ws_bytes, long M, int cap_seg, int img_first, int img_count,
+                             yl_stream_t stream)
+{
+    return filter_raw_impl(raw, F, n_layers, B, C, anchors_px, anchor_mask, conf_thre, ws, ws_bytes, M, cap_seg, img_first,
+                           img_count, stream, 3);
+}
+
+extern "C" int yl_filter_raw_stage(const float *const *raw, const int *F, int n_layers, int B, int C,
+                                   const float *anchors_px, const int *anchor_mask, float conf_thre,
+                                   void *ws, size_t ws_bytes, long M, int cap_seg, int img_first, int img_count,
+                                   int stages, yl_stream_t stream)
+{
+    if (stages < 1 || stages > 3) return YL_ERR_ARG;
+    return filter_raw_impl(raw, F, n_layers, B, C, anchors_px, anchor_mask, conf_thre, ws, ws_bytes, M, cap_seg, img_first,
+                           img_count, stream, stages);
 }
 
 extern "C" int yl_filter_dense(const float *pred, int B, long M, int C, int num_classes, float conf_thre,
