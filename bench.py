@@ -230,6 +230,22 @@ def main():
                "d2h_bytes_per_step": int(rows_per_step * 28 + 3 * B * 4), "steps": args.e2e_steps}
         _cabi.check(L.yl_context_destroy(ctx))
 
+    # ---- multi-GPU: the only exchange is the final all-gather of counts + kept rows (not on the hot path; timed apart) ----
+    gather_ms = None
+    if world > 1:
+        from yolov4_b200.sharded import allgather_detections
+        counts = hp.meta[:B].contiguous()
+        for _ in range(2):
+            allgather_detections(hp.rows, counts)
+        barrier()
+        t0 = time.perf_counter()
+        n_g = 5
+        for _ in range(n_g):
+            out_all = allgather_detections(hp.rows, counts)
+        torch.cuda.synchronize()
+        gather_ms = (time.perf_counter() - t0) / n_g * 1e3
+        assert len(out_all) == world * B
+
     cpu = None
     if rank == 0 and world == 1 and args.cpu_sample > 0:
         threads = os.cpu_count() or 1
@@ -247,7 +263,8 @@ def main():
                                    "(BASELINE configs[1])" % B,
                        "l2": "inputs (495 MB/step) are larger than L2 (126 MB); no flush needed",
                        "timed": "CUDA-graph replay of counter reset + flag + emit + segment NMS (warp tier, big tier) + gather",
-                       "rows_per_step": rows_per_step, "parallelism": "images sharded by rank, no collective on the hot path"},
+                       "rows_per_step": rows_per_step, "parallelism": "images sharded by rank, no collective on the hot path",
+                       "final_allgather_ms": gather_ms},
             "gpu_launches": hp.launches_per_run * args.steps,
             "e2e": e2e,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -52,6 +52,7 @@ struct RawLayer {
 struct RawParams {
     RawLayer layer[3];
     int n_layers, C, cap_seg, img_first;
+    int sparse;            // high thresholds: look at the objectness plane first and skip the class planes of dead vectors
     long M;
     float thr;
     uint4 *cand;
@@ -234,20 +235,37 @@ __device__ __forceinline__ void ldg_stream(const RawParams &P, const RawLayer &L
     const float *cp = base + 5 * (size_t)F2;
     // The objectness plane and the first eight class planes are requested together: the bound needs sigmoid(obj),
     // but the class loads do not, so no load latency is spent with nothing else in flight.
+    // (With a high threshold -- detect setting, conf 0.2 -- almost every box is dead on objectness alone; then the
+    // objectness plane is read first and the class planes of dead vectors are never requested.)
     Vec<VEC> tob, t0[8];
     const int kn0 = min(8, C);
-    if (inb) {
-        tob.load(base + 4 * (size_t)F2);
-#pragma unroll
-        for (int u = 0; u < 8; ++u)
-            if (u < kn0) t0[u].load(cp + (size_t)u * F2);
-    }
     bool any_alive = false;
+    if (P.sparse) {
+        if (inb) tob.load(base + 4 * (size_t)F2);
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) {
-        obj[v] = inb ? spec_sigmoidf(tob.v[v]) : 0.0f;
-        lth[v] = inb ? class_logit_bound(obj[v], thr) : kInf;
-        any_alive |= (lth[v] != kInf);
+        for (int v = 0; v < VEC; ++v) {
+            obj[v] = inb ? spec_sigmoidf(tob.v[v]) : 0.0f;
+            lth[v] = inb ? class_logit_bound(obj[v], thr) : kInf;
+            any_alive |= (lth[v] != kInf);
+        }
+        if (any_alive) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (u < kn0) t0[u].load(cp + (size_t)u * F2);
+        }
+    } else {
+        if (inb) {
+            tob.load(base + 4 * (size_t)F2);
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (u < kn0) t0[u].load(cp + (size_t)u * F2);
+        }
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            obj[v] = inb ? spec_sigmoidf(tob.v[v]) : 0.0f;
+            lth[v] = inb ? class_logit_bound(obj[v], thr) : kInf;
+            any_alive |= (lth[v] != kInf);
+        }
     }
 #pragma unroll
     for (int v = 0; v < VEC; ++v)
@@ -785,6 +803,7 @@ static int filter_raw_impl(const float *const *raw, const int *F, int n_layers, 
     float *objtab = (float *)(w + L.off_obj);
     RawParams base;
     base.C = C; base.cap_seg = cap_seg; base.img_first = img_first; base.M = M; base.thr = conf_thre;
+    base.sparse = conf_thre >= 0.02f ? 1 : 0;     // sigmoid(obj) >= 0.02 is rare for background cells (obj logit >= -3.9)
     base.cand = cand; base.seg_count = seg_count; base.boxtab = boxtab; base.objtab = objtab; base.n_layers = 0;
     base.flags = (unsigned *)(w + L.off_flags); base.M4 = L.M4; base.BM4 = (long)B * L.M4;
     RawParams Pt = base, Pl = base;                 // Pt: persistent TMA kernel (TMA scales first, scalar scales last); Pl: LDG kernel
