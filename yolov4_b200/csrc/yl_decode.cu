@@ -18,9 +18,9 @@ k_decode_dense(const float *__restrict__ raw, int Fw, int F2, int C, float strid
                float aw0, float ah0, float aw1, float ah1, float aw2, float ah2,
                float *__restrict__ out, long rows_per_image, long row_offset)
 {
-    extern __shared__ float tile[];            // [DD_TP][nchp], nchp odd -> conflict-free transposed stores
+    extern __shared__ __align__(16) float tile[];   // [DD_TP][nch]: the output layout itself (odd nch, e.g. 85: conflict-free stores)
     const int nch = 5 + C;
-    const int nchp = nch | 1;
+    const int nchp = nch;
     const int ba = blockIdx.y;
     const int b = ba / 3, a = ba - 3 * b;
     const int p0 = blockIdx.x * DD_TP;
@@ -33,65 +33,102 @@ k_decode_dense(const float *__restrict__ raw, int Fw, int F2, int C, float strid
         const int p = p0 + pl;
         const int gy = p / Fw, gx = p - gy * Fw;
         const float *src = raw + ((size_t)ba * nch) * F2 + p;
-        for (int k = kr; k < nch; k += DD_THREADS / DD_TP) {
-            const float t = ldg_stream1(src + (size_t)k * F2);
-            float v;
-            if (k == 0) v = __fmul_rn(__fadd_rn(spec_sigmoidf(t), (float)gx), stride);
-            else if (k == 1) v = __fmul_rn(__fadd_rn(spec_sigmoidf(t), (float)gy), stride);
-            else if (k == 2) v = __fmul_rn(__fmul_rn(spec_expf(t), aw), stride);
-            else if (k == 3) v = __fmul_rn(__fmul_rn(spec_expf(t), ah), stride);
-            else v = spec_sigmoidf(t);
-            tile[pl * nchp + k] = v;
+        constexpr int KR = DD_THREADS / DD_TP;                       // channel rows per pass
+        for (int k0 = kr; k0 < nch; k0 += KR * 8) {                  // eight loads in flight per thread, then the math
+            float t[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int k = k0 + KR * u;
+                t[u] = (k < nch) ? ldg_stream1(src + (size_t)k * F2) : 0.0f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int k = k0 + KR * u;
+                if (k < nch) {
+                    float v;
+                    if (k == 0) v = __fmul_rn(__fadd_rn(spec_sigmoidf(t[u]), (float)gx), stride);
+                    else if (k == 1) v = __fmul_rn(__fadd_rn(spec_sigmoidf(t[u]), (float)gy), stride);
+                    else if (k == 2) v = __fmul_rn(__fmul_rn(spec_expf(t[u]), aw), stride);
+                    else if (k == 3) v = __fmul_rn(__fmul_rn(spec_expf(t[u]), ah), stride);
+                    else v = spec_sigmoidf(t[u]);
+                    tile[pl * nchp + k] = v;
+                }
+            }
         }
     }
     __syncthreads();
+    // the tile is a contiguous run of np*nch floats in the output: straight copy, 128-bit where the run is aligned
     float *dst = out + ((size_t)b * rows_per_image + row_offset + (size_t)a * F2 + p0) * nch;
     const int n = np * nch;
-    for (int e = threadIdx.x; e < n; e += DD_THREADS) {
-        const int box = e / nch, k = e - box * nch;
-        dst[e] = tile[box * nchp + k];
+    if ((((uintptr_t)dst) & 15) == 0) {
+        const int n4 = n >> 2;
+        for (int e = threadIdx.x; e < n4; e += DD_THREADS)
+            reinterpret_cast<float4 *>(dst)[e] = reinterpret_cast<const float4 *>(tile)[e];
+        for (int e = (n4 << 2) + threadIdx.x; e < n; e += DD_THREADS) dst[e] = tile[e];
+    } else {
+        for (int e = threadIdx.x; e < n; e += DD_THREADS) dst[e] = tile[e];
     }
 }
 
 constexpr int DT_THREADS = 256;
 
+template <int VEC>
 __global__ void __launch_bounds__(DT_THREADS)
 k_decode_train(const float *__restrict__ raw, int Fw, int F2, int C, long total,
                float aw0, float ah0, float aw1, float ah1, float aw2, float ah2,
                float *__restrict__ output_planar, float *__restrict__ pred_planar)
 {
     const int nch = 5 + C;
-    for (long idx = (long)blockIdx.x * DT_THREADS + threadIdx.x; idx < total; idx += (long)gridDim.x * DT_THREADS) {
+    const long nvec = total / VEC;
+    for (long iv = (long)blockIdx.x * DT_THREADS + threadIdx.x; iv < nvec; iv += (long)gridDim.x * DT_THREADS) {
+        const long idx = iv * VEC;                                            // VEC consecutive elements of one plane
         const long plane = idx / F2;
         const int p = (int)(idx - plane * F2);
         const int ba = (int)(plane / nch);
         const int k = (int)(plane - (long)ba * nch);
-        const float t = raw[idx];
-        float o = t;
-        if (k != 2 && k != 3) o = spec_sigmoidf(t);                          // yololayer.py:105
-        output_planar[idx] = o;
+        Vec<VEC> t;
+        t.load(raw + idx);
+        float o[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) o[v] = (k != 2 && k != 3) ? spec_sigmoidf(t.v[v]) : t.v[v];      // yololayer.py:105
+        if (VEC == 4) *reinterpret_cast<float4 *>(output_planar + idx) = make_float4(o[0], o[1 % VEC], o[2 % VEC], o[3 % VEC]);
+        else output_planar[idx] = o[0];
         if (k < 4) {
             const int a = ba % 3;
-            float v;
-            if (k == 0) v = __fadd_rn(o, (float)(p % Fw));                   // :126
-            else if (k == 1) v = __fadd_rn(o, (float)(p / Fw));              // :129
-            else if (k == 2) v = __fmul_rn(spec_expf(t), (a == 0) ? aw0 : ((a == 1) ? aw1 : aw2));   // :132
-            else v = __fmul_rn(spec_expf(t), (a == 0) ? ah0 : ((a == 1) ? ah1 : ah2));               // :134
-            pred_planar[((size_t)ba * 4 + k) * F2 + p] = v;
+            float pv[VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                const int pp = p + v;
+                if (k == 0) pv[v] = __fadd_rn(o[v], (float)(pp % Fw));                   // :126
+                else if (k == 1) pv[v] = __fadd_rn(o[v], (float)(pp / Fw));              // :129
+                else if (k == 2) pv[v] = __fmul_rn(spec_expf(t.v[v]), (a == 0) ? aw0 : ((a == 1) ? aw1 : aw2));   // :132
+                else pv[v] = __fmul_rn(spec_expf(t.v[v]), (a == 0) ? ah0 : ((a == 1) ? ah1 : ah2));               // :134
+            }
+            float *dst = pred_planar + ((size_t)ba * 4 + k) * F2 + p;
+            if (VEC == 4) *reinterpret_cast<float4 *>(dst) = make_float4(pv[0], pv[1 % VEC], pv[2 % VEC], pv[3 % VEC]);
+            else dst[0] = pv[0];
         }
     }
 }
 
+template <int VEC>
 __global__ void __launch_bounds__(DT_THREADS)
 k_decode_train_bwd(const float *__restrict__ output_planar, const float *__restrict__ grad_out, int F2, int C, long total,
                    float *__restrict__ grad_raw)
 {
     const int nch = 5 + C;
-    for (long idx = (long)blockIdx.x * DT_THREADS + threadIdx.x; idx < total; idx += (long)gridDim.x * DT_THREADS) {
+    const long nvec = total / VEC;
+    for (long iv = (long)blockIdx.x * DT_THREADS + threadIdx.x; iv < nvec; iv += (long)gridDim.x * DT_THREADS) {
+        const long idx = iv * VEC;
         const int k = (int)((idx / F2) % nch);
-        const float g = grad_out[idx];
-        const float o = output_planar[idx];
-        grad_raw[idx] = (k == 2 || k == 3) ? g : (g * (1.0f - o)) * o;     // ATen sigmoid_backward order
+        Vec<VEC> g, o;
+        g.load(grad_out + idx);
+        o.load(output_planar + idx);
+        float r[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) r[v] = (k == 2 || k == 3) ? g.v[v] : (g.v[v] * (1.0f - o.v[v])) * o.v[v];     // ATen sigmoid_backward order
+        if (VEC == 4) *reinterpret_cast<float4 *>(grad_raw + idx) = make_float4(r[0], r[1 % VEC], r[2 % VEC], r[3 % VEC]);
+        else grad_raw[idx] = r[0];
     }
 }
 
@@ -105,8 +142,7 @@ extern "C" int yl_decode_dense(const float *raw, int B, int F, int C, const floa
     if (!raw || !ag || !out || B <= 0 || F <= 0 || C <= 0 || rows_per_image < 3L * F * F + row_offset || row_offset < 0)
         return YL_ERR_ARG;
     const int F2 = F * F;
-    const int nchp = (5 + C) | 1;
-    const size_t smem = sizeof(float) * DD_TP * nchp;
+    const size_t smem = sizeof(float) * DD_TP * (5 + C);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(k_decode_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return YL_ERR_CUDA_BASE + (int)e;
@@ -124,10 +160,16 @@ extern "C" int yl_decode_train(const float *raw, int B, int F, int C, const floa
     if (!raw || !ag || !output_planar || !pred_planar || B <= 0 || F <= 0 || C <= 0) return YL_ERR_ARG;
     const int F2 = F * F;
     const long total = (long)B * 3 * (5 + C) * F2;
-    const long blocks = (total + DT_THREADS - 1) / DT_THREADS;
-    const int grid = (int)(blocks < 148L * 32 ? blocks : 148L * 32);
-    k_decode_train<<<grid, DT_THREADS, 0, (cudaStream_t)stream>>>(raw, F, F2, C, total, ag[0], ag[1], ag[2], ag[3], ag[4],
-                                                                  ag[5], output_planar, pred_planar);
+    // planes are 16-byte aligned when F*F is a multiple of 4 and the bases are: then four elements per thread
+    const bool vec4 = (F2 % 4 == 0) && (((uintptr_t)raw | (uintptr_t)output_planar | (uintptr_t)pred_planar) % 16 == 0);
+    const long blocks = (total / (vec4 ? 4 : 1) + DT_THREADS - 1) / DT_THREADS;
+    const int grid = (int)(blocks < 148L * 64 ? blocks : 148L * 64);
+    if (vec4)
+        k_decode_train<4><<<grid, DT_THREADS, 0, (cudaStream_t)stream>>>(raw, F, F2, C, total, ag[0], ag[1], ag[2], ag[3], ag[4],
+                                                                         ag[5], output_planar, pred_planar);
+    else
+        k_decode_train<1><<<grid, DT_THREADS, 0, (cudaStream_t)stream>>>(raw, F, F2, C, total, ag[0], ag[1], ag[2], ag[3], ag[4],
+                                                                         ag[5], output_planar, pred_planar);
     YL_LAUNCH_CHECK();
     return YL_OK;
 }
@@ -138,9 +180,11 @@ extern "C" int yl_decode_train_backward(const float *output_planar, const float 
     if (!output_planar || !grad_out_planar || !grad_raw || B <= 0 || F <= 0 || C <= 0) return YL_ERR_ARG;
     const int F2 = F * F;
     const long total = (long)B * 3 * (5 + C) * F2;
-    const long blocks = (total + DT_THREADS - 1) / DT_THREADS;
-    const int grid = (int)(blocks < 148L * 32 ? blocks : 148L * 32);
-    k_decode_train_bwd<<<grid, DT_THREADS, 0, (cudaStream_t)stream>>>(output_planar, grad_out_planar, F2, C, total, grad_raw);
+    const bool vec4 = (F2 % 4 == 0) && (((uintptr_t)output_planar | (uintptr_t)grad_out_planar | (uintptr_t)grad_raw) % 16 == 0);
+    const long blocks = (total / (vec4 ? 4 : 1) + DT_THREADS - 1) / DT_THREADS;
+    const int grid = (int)(blocks < 148L * 64 ? blocks : 148L * 64);
+    if (vec4) k_decode_train_bwd<4><<<grid, DT_THREADS, 0, (cudaStream_t)stream>>>(output_planar, grad_out_planar, F2, C, total, grad_raw);
+    else k_decode_train_bwd<1><<<grid, DT_THREADS, 0, (cudaStream_t)stream>>>(output_planar, grad_out_planar, F2, C, total, grad_raw);
     YL_LAUNCH_CHECK();
     return YL_OK;
 }

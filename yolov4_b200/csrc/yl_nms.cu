@@ -27,6 +27,12 @@ __device__ __forceinline__ bool suppresses_pos(const float4 &a, float area_a, co
     const float tlx = fmaxf(a.x, b.x), tly = fmaxf(a.y, b.y);
     const float brx = fminf(a.z, b.z), bry = fminf(a.w, b.w);
     if (!(tlx < brx && tly < bry)) return false;
+    // Overlapping boxes have positive extents, so fl(inter) <= min(area) and union >= max(area): boxes whose areas
+    // differ by more than the threshold ratio cannot reach it (common across anchor scales), no matter the overlap.
+    {
+        const float amin = fminf(area_a, area_b), amax = fmaxf(area_a, area_b);
+        if (amax < 3.0e38f && amin < 0.999f * thr * amax) return false;
+    }
     const float inter = __fmul_rn(__fsub_rn(brx, tlx), __fsub_rn(bry, tly));
     const float uni = __fsub_rn(__fadd_rn(area_a, area_b), inter);
     // fl(inter/uni) >= thr is decided without the division when inter is not within 0.1% of thr*uni (the quotient's
@@ -200,7 +206,11 @@ __device__ int greedy_nms(Store &s, int n, float thr, unsigned short *kept_s, un
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int SMALL_R = 256;
 constexpr int SMALL_W = SMALL_R / 32;
-constexpr int SMALL_THREADS = 128;
+#ifndef YL_SMALL_THREADS
+#define YL_SMALL_THREADS 128
+#endif
+constexpr int SMALL_THREADS = YL_SMALL_THREADS;
+constexpr int SMALL_EPT = SMALL_R / SMALL_THREADS;      // records per thread, at most
 
 // Conservative 16-bit image of a (sanitised) box for the pair prefilter: corners are rounded outwards (floor for x1,y1,
 // ceil for x2,y2), clamped to +-16384 px and biased to 15-bit unsigned, two per 32-bit word.  Rounding and clamping are
@@ -306,11 +316,11 @@ k_segment_nms_small(uint4 *__restrict__ cand, const unsigned *__restrict__ seg_c
     const bool pos = thr > 0.0f;
 
     // load (at most two records per thread), start the box gathers, then rank
-    unsigned long long key[2];
-    unsigned conf[2], row[2];
-    float4 bx[2];
+    unsigned long long key[SMALL_EPT];
+    unsigned conf[SMALL_EPT], row[SMALL_EPT];
+    float4 bx[SMALL_EPT];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < SMALL_EPT; ++u) {
         const int i = tid + u * SMALL_THREADS;
         key[u] = ~0ull; conf[u] = 0u; row[u] = 0u;
         if (i < n) {
@@ -321,18 +331,21 @@ k_segment_nms_small(uint4 *__restrict__ cand, const unsigned *__restrict__ seg_c
         }
     }
 #pragma unroll
-    for (int u = 0; u < 2; ++u)
+    for (int u = 0; u < SMALL_EPT; ++u)
         if (tid + u * SMALL_THREADS < n) bx[u] = boxes[row[u]];
     __syncthreads();
-    int rank[2] = {0, 0};
+    int rank[SMALL_EPT];
+#pragma unroll
+    for (int u = 0; u < SMALL_EPT; ++u) rank[u] = 0;
     const int wbase = tid & ~31;                                // first element index of this warp (warp-uniform bounds below)
     // keys beyond n were never written: pad the tail of the last 16-byte pair so the 2-wide loop may read it
     if (tid == 0 && (n & 1)) sh_key[n] = ~0ull;
     __syncthreads();
-    if (wbase < n) rank[0] = rank_of(sh_key, n, key[0]);
-    if (wbase + SMALL_THREADS < n) rank[1] = rank_of(sh_key, n, key[1]);
 #pragma unroll
-    for (int u = 0; u < 2; ++u)
+    for (int u = 0; u < SMALL_EPT; ++u)
+        if (wbase + u * SMALL_THREADS < n) rank[u] = rank_of(sh_key, n, key[u]);          // warp-uniform bound
+#pragma unroll
+    for (int u = 0; u < SMALL_EPT; ++u)
         if (tid + u * SMALL_THREADS < n) {
             const int r = rank[u];
             sh_row[r] = row[u]; sh_conf[r] = conf[u];
