@@ -129,6 +129,18 @@ int yl_build_target(const float *pred, const long *pred_strides, const float *la
                     yl_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * N1  per-detection epilogue of the reference's callers
+ *   mode 0: validate()  yolo/engine/build.py:146-164 + yolobox2xywh (yolo/util/utils.py:281-309), float64 like the Python loop
+ *           out row = (image_id, category_id, x, y, w, h, score = obj_conf*cls_conf)
+ *   mode 1: detect.parse_info()  detect.py:171-179 + yolobox2yxyx (utils.py:312-340), fp32 box arithmetic
+ *           out row = (image_id, category_id, y1, x1, y2, x2, cls_conf)
+ *   rows [K,7] fp32 (postprocess output rows back to back), row_image [K] image index of each row,
+ *   img_info [n_img,4] = (src_h, src_w, dst_h, dst_w) float64, image_ids [n_img] int64, class_ids [n_classes] int32 (all device)
+ * --------------------------------------------------------------------------------------------------------- */
+int yl_coco_rows(const float *rows, const int *row_image, long K, const double *img_info, const long long *image_ids,
+                 const int *class_ids, int n_classes, int mode, double *out, yl_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * Host-buffer entry (what a non-Python caller binds; also the bench's end-to-end leg): raw head tensors in
  * HOST memory -> detections in HOST memory.  The context owns device staging buffers, workspace, streams and
  * pinned bounce buffers; H2D copies, kernels and the D2H of rows/counts are all inside the call.

@@ -234,13 +234,48 @@ def gen_build_target():
     np.savez_compressed(os.path.join(HERE, "build_target.npz"), **out)
 
 
+def gen_epilogue():
+    """N1: the per-detection arithmetic of validate() (engine/build.py:146-164, importable parts: utils.yolobox2xywh) and of
+    detect.parse_info (detect.py:171-179, utils.yolobox2yxyx).  engine/build.py itself needs apex + pycocotools, so the
+    five lines of its loop body are driven here around the reference's own converter functions."""
+    rng = np.random.RandomState(17)
+    n_img = 3
+    counts = [40, 0, 25]
+    rows = []
+    for k in counts:
+        xy = rng.rand(k, 2).astype(np.float32) * 500
+        wh = rng.rand(k, 2).astype(np.float32) * 100 + 1
+        r = np.concatenate([xy, xy + wh, rng.rand(k, 2).astype(np.float32), rng.randint(0, 80, (k, 1)).astype(np.float32)], 1)
+        rows.append(torch.from_numpy(r.astype(np.float32)))
+    img_info = [[480, 640, 456, 608], [1080, 1920, 342, 608], [333, 500, 405, 608]]      # src_h, src_w, dst_h, dst_w
+    image_ids = [139, 285, 632]
+    class_ids = [int(i * 1.13) + 1 for i in range(80)]                                    # COCO-like sparse category ids
+    coco, det = [], []
+    for b in range(n_img):
+        outputs = rows[b].cpu().data
+        for output in outputs:                                                            # engine/build.py:146-164
+            x1 = float(output[0]); y1 = float(output[1]); x2 = float(output[2]); y2 = float(output[3])
+            label = class_ids[int(output[6])]
+            bbox = ref_utils.yolobox2xywh((y1, x1, y2, x2), img_info[b][:4])
+            score = float(output[4].data.item() * output[5].data.item())
+            coco.append([image_ids[b], label] + bbox + [score])
+        for x1, y1, x2, y2, conf, cls_conf, cls_pred in rows[b].numpy():                  # detect.py:171-179
+            box = ref_utils.yolobox2yxyx([y1, x1, y2, x2], img_info[b][:4])
+            det.append([b, class_ids[int(cls_pred)]] + [float(v) for v in box] + [float(cls_conf.item())])
+    out = {"rows": np.concatenate([r.numpy() for r in rows], 0), "counts": np.array(counts, np.int32),
+           "img_info": np.array(img_info, np.float64), "image_ids": np.array(image_ids, np.int64),
+           "class_ids": np.array(class_ids, np.int32), "coco": np.array(coco, np.float64), "detect": np.array(det, np.float64)}
+    np.savez_compressed(os.path.join(HERE, "epilogue.npz"), **out)
+    print("epilogue.npz", out["coco"].shape, out["detect"].shape)
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
-    gen_decode()
-    gen_postprocess()
-    gen_nms()
-    gen_iou()
-    gen_build_target()
+    only = sys.argv[1:]
+    for name, fn in (("decode", gen_decode), ("postprocess", gen_postprocess), ("nms", gen_nms), ("iou", gen_iou),
+                     ("build_target", gen_build_target), ("epilogue", gen_epilogue)):
+        if not only or name in only:
+            fn()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

@@ -88,3 +88,25 @@ class YOLOLayer(nn.Module):
             _cabi.check(_cabi.lib().yl_decode_dense(raw.data_ptr(), B, F, self.n_classes, self._anch, float(self.stride),
                                                     res.data_ptr(), self.n_anchors * F * F, 0, _stream()))
         return res
+
+
+def decode_dense_cat(head_outputs, cfg):
+    """The three eval-mode YOLOLayer outputs written straight into one [B, sum 3F^2, 5+C] tensor: the value of
+    `torch.cat((x1, x2, x3), 1)` at yolov4.py:324 without the three intermediate tensors and the cat copy."""
+    C = int(cfg['N_CLASSES'])
+    B = int(head_outputs[0].shape[0])
+    Fs = [int(r.shape[2]) for r in head_outputs]
+    M = sum(3 * f * f for f in Fs)
+    dev = head_outputs[0].device
+    out = torch.empty((B, M, 5 + C), dtype=torch.float32, device=dev)
+    off = 0
+    with torch.cuda.device(dev):
+        for l, r in enumerate(head_outputs):
+            if not r.is_cuda or r.dtype != torch.float32 or r.shape[1] != 3 * (5 + C):
+                raise TypeError("head tensors must be float32 CUDA tensors [B, 3*(5+C), F, F]")
+            s = YOLOLayer.strides[l]
+            anch = _cabi.floats([v / s for i in cfg['ANCHOR_MASK'][l] for v in cfg['ANCHORS'][i]])
+            raw = r.detach().contiguous()
+            _cabi.check(_cabi.lib().yl_decode_dense(raw.data_ptr(), B, Fs[l], C, anch, float(s), out.data_ptr(), M, off, _stream()))
+            off += 3 * Fs[l] * Fs[l]
+    return out
