@@ -407,8 +407,10 @@ __global__ void __launch_bounds__(K1_THREADS, YL_EMIT_MINB)
 k_emit_flagged(const __grid_constant__ RawParams P)
 {
     __shared__ LdgSmem sm;
-    const int ba = P.img_first * 3 + blockIdx.y;
-    int tile = blockIdx.x;
+    // Reverse order of k_flag_raw: the planes that kernel streamed last are still in L2 (126 MB of the 495 MB), so the
+    // flagged logits / box planes of the first tiles handled here are re-read from L2 instead of DRAM.
+    const int ba = P.img_first * 3 + ((int)gridDim.y - 1 - (int)blockIdx.y);
+    int tile = (int)gridDim.x - 1 - (int)blockIdx.x;
     int l = 0;
     while (l < P.n_layers - 1 && tile >= P.layer[l].tiles) { tile -= P.layer[l].tiles; ++l; }
     if (P.layer[l].vec == 4) emit_tile<4, NW>(P, P.layer[l], tile, ba, sm);
