@@ -161,10 +161,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # clocks are sampled from the warm-up through the timed region and the per-kernel timing below (the timed region
+    # itself is only K x 0.26 ms, shorter than nvidia-smi's sampling period for small K)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(args.warmup):
         hp.replay()
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
