@@ -4,9 +4,10 @@
 //                   with multi-label expansion (utils.py:139-184), single pass over the raw head tensor.
 //   k_filter_dense  the same filter over an already decoded [B,M,5+C] tensor (the literal postprocess() input).
 //
-// Both append one record per surviving (box,class) pair to the (image,class) segment cand[(b*C+c)*cap_seg + slot]
-// and store the box once in boxtab/objtab[b*M + row].  Slot order inside a segment is arbitrary (atomics); the NMS
-// stage sorts by the unique key (score, row), so final results are deterministic.
+// Both append one self-contained 32-byte record per surviving (box,class) pair to the (image,class) segment
+// cand[((b*C+c)*cap_seg + slot)*2 + {0,1}] = {score bits, box row, cls_conf bits, obj_conf bits}, {x1, y1, x2, y2}.
+// Slot order inside a segment is arbitrary (atomics); the NMS stage sorts by the unique key (score, row), so final
+// results are deterministic.
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
@@ -57,8 +58,7 @@ struct RawParams {
     float thr;
     uint4 *cand;
     unsigned *seg_count;
-    float4 *boxtab;
-    float *objtab;
+    float *objtab;         // split filter: sigmoid(objectness) of every box, flag kernel -> emit kernel
     unsigned *flags;       // split filter: [NW][B*M4] flag words (see PostLayout)
     long M4;               // row pitch of flags / objtab in split mode (M rounded up to 4)
     long BM4;              // B * M4
@@ -72,6 +72,7 @@ struct EmitWarp {
     unsigned short ent[K1_QCAP];       // bit15 pass | box slot (7b) << 8 | class (7b)
     unsigned cls[K1_QCAP];             // sigmoid(class logit) bits of passing entries
     unsigned any[4], nan[4];           // per box slot: has a surviving pair / has a NaN class logit
+    float4 box[128];                   // decoded corners of the box slots that have a surviving pair
 };
 
 // Decode one box (yololayer.py:150-162) and convert to corners (utils.py:117-126).
@@ -144,12 +145,10 @@ __device__ __forceinline__ void emit_batch(const RawParams &P, const RawLayer &L
             const unsigned wsel = (j == 0) ? lw[0] : ((j == 1) ? lw[1] : ((j == 2) ? lw[2] : lw[3]));
             const int lcs = (j == 0) ? lc[0] : ((j == 1) ? lc[1] : ((j == 2) ? lc[2] : lc[3]));
             const int bs = 32 * j + (int)__fns(wsel, 0, i - lcs + 1);
-            const int p = wp0 + bs;
-            const size_t brow = (size_t)b * P.M4 + (row_base + p);
-            P.boxtab[brow] = decode_box(wbase + bs, F2, Ly.Fw, p, Ly.aw[a], Ly.ah[a], Ly.stride);
-            P.objtab[brow] = sobj[bs];
+            E.box[bs] = decode_box(wbase + bs, F2, Ly.Fw, wp0 + bs, Ly.aw[a], Ly.ah[a], Ly.stride);
         }
     }
+    __syncwarp();
     for (int q = lane; q < total; q += 32) {
         const unsigned en = E.ent[q];
         const int bs = (en >> 8) & 0x7F;
@@ -159,9 +158,12 @@ __device__ __forceinline__ void emit_batch(const RawParams &P, const RawLayer &L
             const float s = __fadd_rn(__fmul_rn(sobj[bs], cls), 0.0f);      // +0 canonicalises -0
             const unsigned seg = (unsigned)(b * C + k);
             const unsigned slot = atomicAdd(&P.seg_count[seg], 1u);
-            if (slot < (unsigned)P.cap_seg)
-                P.cand[(size_t)seg * P.cap_seg + slot] =
-                    make_uint4(__float_as_uint(s), (unsigned)(row_base + wp0 + bs), __float_as_uint(cls), 0u);
+            if (slot < (unsigned)P.cap_seg) {
+                uint4 *r = P.cand + ((size_t)seg * P.cap_seg + slot) * 2;
+                const float4 bx = E.box[bs];
+                r[0] = make_uint4(__float_as_uint(s), (unsigned)(row_base + wp0 + bs), __float_as_uint(cls), __float_as_uint(sobj[bs]));
+                r[1] = make_uint4(__float_as_uint(bx.x), __float_as_uint(bx.y), __float_as_uint(bx.z), __float_as_uint(bx.w));
+            }
         }
     }
     __syncwarp();
@@ -668,8 +670,7 @@ constexpr int KD_MAXJ = (5 + YL_MAX_CLASSES + 31) / 32;
 __global__ void __launch_bounds__(KD_THREADS)
 k_filter_dense(const float *__restrict__ pred, long M, long M4, int C, int num_classes, float thr, int cap_seg,
                int img_first, long n_rows,
-               uint4 *__restrict__ cand, unsigned *__restrict__ seg_count,
-               float4 *__restrict__ boxtab, float *__restrict__ objtab)
+               uint4 *__restrict__ cand, unsigned *__restrict__ seg_count)
 {
     const int lane = threadIdx.x & 31;
     const long wid = ((long)blockIdx.x * KD_THREADS + threadIdx.x) >> 5;
@@ -708,14 +709,11 @@ k_filter_dense(const float *__restrict__ pred, long M, long M4, int C, int num_c
             any |= pass[j];
         }
         if (!__any_sync(0xFFFFFFFFu, any)) continue;
-        const size_t brow = (size_t)b * M4 + row;
         const float cx = __shfl_sync(0xFFFFFFFFu, e[0], 0), cy = __shfl_sync(0xFFFFFFFFu, e[0], 1);
         const float w = __shfl_sync(0xFFFFFFFFu, e[0], 2), h = __shfl_sync(0xFFFFFFFFu, e[0], 3);
-        if (lane == 0) {
-            const float hw = __fmul_rn(w, 0.5f), hh = __fmul_rn(h, 0.5f);      // utils.py:117-126
-            boxtab[brow] = make_float4(__fsub_rn(cx, hw), __fsub_rn(cy, hh), __fadd_rn(cx, hw), __fadd_rn(cy, hh));
-            objtab[brow] = obj;
-        }
+        const float hw = __fmul_rn(w, 0.5f), hh = __fmul_rn(h, 0.5f);          // utils.py:117-126
+        const uint4 corners = make_uint4(__float_as_uint(__fsub_rn(cx, hw)), __float_as_uint(__fsub_rn(cy, hh)),
+                                         __float_as_uint(__fadd_rn(cx, hw)), __float_as_uint(__fadd_rn(cy, hh)));
 #pragma unroll
         for (int j = 0; j < KD_MAXJ; ++j)
             if (pass[j]) {
@@ -723,8 +721,11 @@ k_filter_dense(const float *__restrict__ pred, long M, long M4, int C, int num_c
                 const float s = __fadd_rn(__fmul_rn(obj, e[j]), 0.0f);        // nms score = obj*cls (utils.py:209)
                 const unsigned seg = (unsigned)(b * C + k);
                 const unsigned slot = atomicAdd(&seg_count[seg], 1u);
-                if (slot < (unsigned)cap_seg)
-                    cand[(size_t)seg * cap_seg + slot] = make_uint4(__float_as_uint(s), row, __float_as_uint(e[j]), 0u);
+                if (slot < (unsigned)cap_seg) {
+                    uint4 *r = cand + ((size_t)seg * cap_seg + slot) * 2;
+                    r[0] = make_uint4(__float_as_uint(s), row, __float_as_uint(e[j]), __float_as_uint(obj));
+                    r[1] = corners;
+                }
             }
     }
 }
@@ -801,12 +802,11 @@ static int filter_raw_impl(const float *const *raw, const int *F, int n_layers, 
     char *w = (char *)ws;
     unsigned *seg_count = (unsigned *)(w + L.off_seg_count);
     uint4 *cand = (uint4 *)(w + L.off_cand);
-    float4 *boxtab = (float4 *)(w + L.off_box);
     float *objtab = (float *)(w + L.off_obj);
     RawParams base;
     base.C = C; base.cap_seg = cap_seg; base.img_first = img_first; base.M = M; base.thr = conf_thre;
     base.sparse = conf_thre >= 0.02f ? 1 : 0;     // sigmoid(obj) >= 0.02 is rare for background cells (obj logit >= -3.9)
-    base.cand = cand; base.seg_count = seg_count; base.boxtab = boxtab; base.objtab = objtab; base.n_layers = 0;
+    base.cand = cand; base.seg_count = seg_count; base.objtab = objtab; base.n_layers = 0;
     base.flags = (unsigned *)(w + L.off_flags); base.M4 = L.M4; base.BM4 = (long)B * L.M4;
     RawParams Pt = base, Pl = base;                 // Pt: persistent TMA kernel (TMA scales first, scalar scales last); Pl: LDG kernel
     RawLayer lay[3];
@@ -946,7 +946,7 @@ extern "C" int yl_filter_dense(const float *pred, int B, long M, int C, int num_
     const int grid = (int)(blocks_needed < 148L * 64 ? blocks_needed : 148L * 64);
     k_filter_dense<<<grid, KD_THREADS, 0, (cudaStream_t)stream>>>(
         pred, M, L.M4, C, num_classes, conf_thre, cap_seg, img_first, n_rows, (uint4 *)(w + L.off_cand),
-        (unsigned *)(w + L.off_seg_count), (float4 *)(w + L.off_box), (float *)(w + L.off_obj));
+        (unsigned *)(w + L.off_seg_count));
     YL_LAUNCH_CHECK();
     return YL_OK;
 }

@@ -1,13 +1,19 @@
 // yl_nms.cu -- back end of the postprocess pipeline.
 //
-//   k_segment_nms   one CTA per (image,class) candidate segment: sort by (score desc, box row desc)
-//                   [utils.py:58 with stable tie order], greedy NMS dropping a box when IoU >= thr with any
-//                   already kept box [utils.py:67-84], kept records compacted to the front of the segment.
-//   k_gather_rows   class-ascending concatenation of the kept rows of an image [utils.py:191-220] into
-//                   out_rows[b] = (x1,y1,x2,y2,obj,cls_conf,cls) and the per-image counts.
+//   k_segment_nms_bins  one CTA per (image,class) candidate segment of up to SMALL_R records: sort by
+//                       (score desc, box row desc) [utils.py:58 with stable tie order], greedy NMS dropping a box when
+//                       IoU >= thr with any already kept box [utils.py:67-84]; the kept detections are written as
+//                       finished 7-float rows at the front of the segment.
+//   k_segment_nms_big   persistent CTAs over the queue of segments the small tier passes on (more than SMALL_R
+//                       candidates, dense overlap graphs, thr <= 0): bitonic sort + 64-wide chunked bitmask NMS in
+//                       shared memory (<= SMEM_R) or in place in global memory (degenerate all-ties inputs).
+//   k_gather_rows       class-ascending concatenation of the kept rows of an image [utils.py:191-220] into
+//                       out_rows[b] = (x1,y1,x2,y2,obj,cls_conf,cls) and the per-image counts.
 //
-// Segments up to SMEM_R candidates are processed entirely in shared memory; larger ones (degenerate inputs
-// such as the all-ties random-init case) run the same algorithm in place in global memory.
+// Candidate record (written by the filter kernels, yl_filter.cu): two uint4,
+//   A = {score bits, box row, cls_conf bits, obj_conf bits}    B = {x1, y1, x2, y2}
+// so a segment is self-contained and the back end reads nothing but its own 32-byte records.
+#include <math.h>
 #include <stdlib.h>
 
 #include "yl_common.cuh"
@@ -66,43 +72,425 @@ __device__ __forceinline__ float4 sanitise(const float4 &b)
     return b;
 }
 
-// ---- storage back ends ------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 as_float4(const uint4 &u)
+{
+    return make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
+}
+
+// One finished output row (utils.py:177-184): (x1, y1, x2, y2, obj_conf, cls_conf, cls_idx as float).
+__device__ __forceinline__ void store_row(float *o, const float4 &box, unsigned conf_bits, unsigned obj_bits, float fc)
+{
+    o[0] = box.x; o[1] = box.y; o[2] = box.z; o[3] = box.w;
+    o[4] = __uint_as_float(obj_bits); o[5] = __uint_as_float(conf_bits); o[6] = fc;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Small tier (the common case: ~150 candidates per (image,class) at conf 1e-4).  Everything in ~24 KB of shared memory.
+//   1. rank sort on the 32-bit score key (LDS.128 per four keys, one compare + predicated add per key); if two records
+//      tie on the score the ranks collide, which is detected, and the segment is ranked again on the unique 64-bit key
+//      (score, row);
+//   2. candidate pairs by table lookup instead of an all-pairs loop: boxes are binned on x1, x2, y1, y2 (NBIN bins over
+//      the segment's coordinate range) and on log2(area) (4 bins per octave); six prefix tables hold, per bin, the set
+//      (bitmask over sorted positions) of boxes that CANNOT overlap / reach the IoU threshold with a box of that bin:
+//         x1_i > x2_j | x2_i < x1_j | y1_i > y2_j | y2_i < y1_j | area_i >> area_j | area_i << area_j
+//      so the candidate set of row j is one 6-way OR per 64 earlier boxes.  Binning is monotone, hence conservative: a
+//      pair that overlaps (tl < br on both axes) and whose area ratio allows IoU >= thr is never excluded;
+//   3. the surviving (i, j) pairs (~2 % of all pairs) are queued, then tested exactly by all threads (no divergence);
+//   4. pairs with IoU >= thr set a bit in the transposed suppression matrix T[j]; one warp walks only the rows that
+//      have such a bit, in score order: kept[j] = (T[j] & kept) == 0                       (utils.py:67-84);
+//   5. the kept detections are staged in shared memory and stored as one contiguous run of 7-float rows.
+// Segments with more than SMALL_R candidates, with more queued pairs than the queue holds, or with thr <= 0 (where
+// every pair must go through the literal NaN-propagating formula) are passed on to the big tier.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int SMALL_R = 256;
+constexpr int SMALL_W = SMALL_R / 32;
+constexpr int SMALL_THREADS = 128;
+constexpr int SMALL_WARPS = SMALL_THREADS / 32;
+constexpr int SMALL_EPT = SMALL_R / SMALL_THREADS;      // records per thread, at most
+constexpr int NBIN = 64;
+#ifndef YL_NMS_QCAP
+#define YL_NMS_QCAP 512
+#endif
+constexpr int QCAP_W = YL_NMS_QCAP;                     // queued pairs per warp
+#ifndef YL_NMS_MINB
+#define YL_NMS_MINB 9
+#endif
+constexpr int AREA_BIN_OFF = (127 + 4) << 2;            // float bits >> 21 of 16.0f: areas below 16 px^2 share bin 0
+
+struct alignas(16) BinsSmem {
+    union {
+        struct {
+            unsigned key[SMALL_R + 4];                  // score key per record (record order), padded for the 4-wide loop
+            unsigned pad_[4];
+            unsigned long long k64[SMALL_R + 2];        // tie fallback: (score key, ~row)
+        } s;
+        unsigned short queue[SMALL_WARPS][QCAP_W];      // (j << 8) | i candidate pairs, one queue per warp
+    } a;
+    float4 box[SMALL_R];                                // sorted
+    uint2 co[SMALL_R];                                  // sorted {cls_conf bits, obj_conf bits}
+    unsigned bins[SMALL_R];                             // sorted: bx1 | bx2<<6 | by1<<12 | by2<<18 | barea<<24 | invalid<<31
+    union {
+        unsigned long long tab[6][SMALL_W / 2][NBIN + 1];   // exclusion sets per bin, two 32-box words per entry (+1: conflict-free scan)
+        unsigned T[SMALL_R][SMALL_W];                   // transposed suppression matrix
+        float stage[SMALL_R * 7];                       // finished rows
+    } b;
+    unsigned char owner[SMALL_R];
+    float red[2][SMALL_WARPS];
+    unsigned qn[SMALL_WARPS];
+    unsigned dirty[SMALL_W], keptw[SMALL_W], pref[SMALL_W + 1];
+};
+
+// Number of keys below `key`; keys beyond n are padded with 0xFFFFFFFF up to a multiple of four.
+__device__ __forceinline__ int rank32(const unsigned *sh_key, int n, unsigned key)
+{
+    int r = 0;
+    const uint4 *k4 = reinterpret_cast<const uint4 *>(sh_key);
+    const int n4 = (n + 3) >> 2;
+#pragma unroll 4
+    for (int j = 0; j < n4; ++j) {
+        const uint4 k = k4[j];
+        asm("{\n\t.reg .pred p, q, r, s;\n\t"
+            "setp.lt.u32 p, %1, %5;\n\tsetp.lt.u32 q, %2, %5;\n\tsetp.lt.u32 r, %3, %5;\n\tsetp.lt.u32 s, %4, %5;\n\t"
+            "@p add.s32 %0, %0, 1;\n\t@q add.s32 %0, %0, 1;\n\t@r add.s32 %0, %0, 1;\n\t@s add.s32 %0, %0, 1;\n\t}"
+            : "+r"(r) : "r"(k.x), "r"(k.y), "r"(k.z), "r"(k.w), "r"(key));
+    }
+    return r;
+}
+
+// Number of keys below `key` (keys are unique): LDS.128 per two keys, one 64-bit compare + predicated add per key.
+__device__ __forceinline__ int rank_of(const unsigned long long *sh_key, int n, unsigned long long key)
+{
+    int r = 0;
+    const ulonglong2 *k2 = reinterpret_cast<const ulonglong2 *>(sh_key);
+    const int n2 = (n + 1) >> 1;
+#pragma unroll 4
+    for (int j = 0; j < n2; ++j) {
+        const ulonglong2 k = k2[j];
+        asm("{\n\t.reg .pred p, q;\n\tsetp.lt.u64 p, %1, %3;\n\tsetp.lt.u64 q, %2, %3;\n\t@p add.s32 %0, %0, 1;\n\t@q add.s32 %0, %0, 1;\n\t}"
+            : "+r"(r) : "l"(k.x), "l"(k.y), "l"(key));
+    }
+    return r;
+}
+
+__device__ __forceinline__ int coord_bin(float v, float lo, float scale)
+{
+    // monotone in v: fp subtraction, multiplication by a non-negative constant, floor and clamping all are
+    const int q = __float2int_rd(__fmul_rn(__fsub_rn(v, lo), scale));      // saturates on +-inf, 0 on NaN
+    return min(max(q, 0), NBIN - 1);
+}
+
+__global__ void __launch_bounds__(SMALL_THREADS, YL_NMS_MINB)
+k_segment_nms_bins(uint4 *__restrict__ cand, const unsigned *__restrict__ seg_count, unsigned *__restrict__ kept_count,
+                   int C, int cap_seg, float thr, int area_k, int seg_first,
+                   unsigned *__restrict__ big_count, unsigned *__restrict__ big_list)
+{
+    __shared__ BinsSmem S;
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int seg = seg_first + blockIdx.x;
+    const unsigned cnt = seg_count[seg];
+    if (cnt == 0u) return;                                      // kept_count was zeroed by yl_post_reset
+    if (cnt > (unsigned)cap_seg) return;                        // overflow: reported through meta[], caller re-runs
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (cnt > (unsigned)SMALL_R || !(thr > 0.0f)) {
+        if (tid == 0) big_list[atomicAdd(big_count, 1u)] = (unsigned)seg;
+        return;
+    }
+    const int n = (int)cnt;
+    const int nw = (n + 31) >> 5, nwp = (nw + 1) >> 1;
+    uint4 *rec = cand + (size_t)seg * cap_seg * 2;
+
+    // ---- 1. records -> registers; score keys -> shared memory; coordinate range of the segment ----
+    uint4 ra[SMALL_EPT];
+    float4 rb[SMALL_EPT];
+#pragma unroll
+    for (int u = 0; u < SMALL_EPT; ++u) {
+        const int e = tid + u * SMALL_THREADS;
+        ra[u] = make_uint4(0u, 0u, 0u, 0u);
+        rb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e < n) { ra[u] = rec[2 * e]; rb[u] = as_float4(rec[2 * e + 1]); }
+    }
+    {
+        // zero the exclusion tables while the loads are in flight
+        uint4 *z = reinterpret_cast<uint4 *>(&S.b.tab[0][0][0]);
+        constexpr int NZ = (int)(sizeof(S.b.tab) / sizeof(uint4));
+        for (int i = tid; i < NZ; i += SMALL_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (tid < SMALL_WARPS) S.qn[tid] = 0u;
+        if (tid < SMALL_W) S.dirty[tid] = 0u;
+    }
+    unsigned key[SMALL_EPT];
+    bool valid[SMALL_EPT];
+    float lo = kInf, hi = -kInf;
+#pragma unroll
+    for (int u = 0; u < SMALL_EPT; ++u) {
+        const int e = tid + u * SMALL_THREADS;
+        key[u] = 0xFFFFFFFFu;
+        valid[u] = false;
+        if (e < n) {
+            key[u] = score_desc_bits(ra[u].x);
+            S.a.s.key[e] = key[u];
+            // only boxes with positive extents (hence no NaN) can overlap anything (suppresses_pos: tl < br on both axes)
+            valid[u] = rb[u].x < rb[u].z && rb[u].y < rb[u].w;
+            if (valid[u]) { lo = fminf(lo, fminf(rb[u].x, rb[u].y)); hi = fmaxf(hi, fmaxf(rb[u].z, rb[u].w)); }
+        }
+    }
+    if (tid < 4) S.a.s.key[n + tid] = 0xFFFFFFFFu;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fminf(lo, __shfl_xor_sync(FULL, lo, o));
+        hi = fmaxf(hi, __shfl_xor_sync(FULL, hi, o));
+    }
+    if (lane == 0) { S.red[0][warp] = lo; S.red[1][warp] = hi; }
+    __syncthreads();
+
+    // ---- 2. rank ----
+    const int wbase = tid & ~31;                                // warp-uniform bounds below
+    int rank[SMALL_EPT];
+#pragma unroll
+    for (int u = 0; u < SMALL_EPT; ++u) {
+        rank[u] = 0;
+        if (wbase + u * SMALL_THREADS < n) rank[u] = rank32(S.a.s.key, n, key[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < SMALL_EPT; ++u) {
+        const int e = tid + u * SMALL_THREADS;
+        if (e < n) S.owner[rank[u]] = (unsigned char)e;
+    }
+    __syncthreads();
+    {
+        bool coll = false;
+#pragma unroll
+        for (int u = 0; u < SMALL_EPT; ++u) {
+            const int e = tid + u * SMALL_THREADS;
+            if (e < n) coll |= (S.owner[rank[u]] != (unsigned char)e);
+        }
+        if (__syncthreads_or(coll)) {
+            // equal scores inside the segment: the order is (score desc, row desc), decided on the unique 64-bit key
+            unsigned long long k64[SMALL_EPT];
+#pragma unroll
+            for (int u = 0; u < SMALL_EPT; ++u) {
+                const int e = tid + u * SMALL_THREADS;
+                k64[u] = ~0ull;
+                if (e < n) { k64[u] = ((unsigned long long)key[u] << 32) | (unsigned)(~ra[u].y); S.a.s.k64[e] = k64[u]; }
+            }
+            if (tid == 0 && (n & 1)) S.a.s.k64[n] = ~0ull;
+            __syncthreads();
+#pragma unroll
+            for (int u = 0; u < SMALL_EPT; ++u)
+                if (wbase + u * SMALL_THREADS < n) rank[u] = rank_of(S.a.s.k64, n, k64[u]);
+        }
+    }
+
+    // ---- 3. sorted arrays, bins, table inserts ----
+    {
+        lo = fminf(fminf(S.red[0][0], S.red[0][1]), fminf(S.red[0][2], S.red[0][3]));
+        hi = fmaxf(fmaxf(S.red[1][0], S.red[1][1]), fmaxf(S.red[1][2], S.red[1][3]));
+        lo = fmaxf(lo, -1.0e6f);
+        hi = fminf(hi, 1.0e6f);
+        float scale = __fdiv_rn((float)NBIN, __fsub_rn(hi, lo));
+        if (!(scale > 0.0f && scale < 3.0e38f)) scale = 0.0f;  // empty / degenerate range: one bin, nothing is excluded
+#pragma unroll
+        for (int u = 0; u < SMALL_EPT; ++u) {
+            const int e = tid + u * SMALL_THREADS;
+            if (e < n) {
+                const int r = rank[u];
+                S.box[r] = rb[u];
+                S.co[r] = make_uint2(ra[u].z, ra[u].w);
+                const unsigned bit = 1u << (r & 31);
+                const int wp = r >> 6, half = (r >> 5) & 1;
+                unsigned bn = 0x80000000u;
+                if (valid[u]) {
+                    const int bx1 = coord_bin(rb[u].x, lo, scale), bx2 = coord_bin(rb[u].z, lo, scale);
+                    const int by1 = coord_bin(rb[u].y, lo, scale), by2 = coord_bin(rb[u].w, lo, scale);
+                    const int ab = min(max((int)(__float_as_uint(box_area(rb[u])) >> 21) - AREA_BIN_OFF, 0), NBIN - 1);
+                    bn = (unsigned)bx1 | ((unsigned)bx2 << 6) | ((unsigned)by1 << 12) | ((unsigned)by2 << 18) | ((unsigned)ab << 24);
+                    // tab[0][.][b] (suffix-OR) = { i : bx1_i - 1 >= b }  -> lookup at bx2_j gives x1_i > x2_j (in bins)
+                    // tab[1][.][b] (prefix-OR) = { i : bx2_i + 1 <= b }  -> lookup at bx1_j gives x2_i < x1_j
+                    if (bx1 >= 1) atomicOr(reinterpret_cast<unsigned *>(&S.b.tab[0][wp][bx1 - 1]) + half, bit);
+                    if (bx2 + 1 < NBIN) atomicOr(reinterpret_cast<unsigned *>(&S.b.tab[1][wp][bx2 + 1]) + half, bit);
+                    if (by1 >= 1) atomicOr(reinterpret_cast<unsigned *>(&S.b.tab[2][wp][by1 - 1]) + half, bit);
+                    if (by2 + 1 < NBIN) atomicOr(reinterpret_cast<unsigned *>(&S.b.tab[3][wp][by2 + 1]) + half, bit);
+                    // tab[4][.][b] (suffix-OR) = { i : ab_i - K >= b }   -> lookup at ab_j gives area_i too large for IoU >= thr
+                    // tab[5][.][b] (prefix-OR) = { i : ab_i + K <= b }   -> lookup at ab_j gives area_i too small
+                    if (ab - area_k >= 0) atomicOr(reinterpret_cast<unsigned *>(&S.b.tab[4][wp][ab - area_k]) + half, bit);
+                    if (ab + area_k < NBIN) atomicOr(reinterpret_cast<unsigned *>(&S.b.tab[5][wp][ab + area_k]) + half, bit);
+                } else {
+                    atomicOr(reinterpret_cast<unsigned *>(&S.b.tab[1][wp][0]) + half, bit);     // in every prefix set: never a candidate
+                }
+                S.bins[r] = bn;
+            }
+        }
+    }
+    __syncthreads();
+    // prefix / suffix OR over the bins: 6 tables x nwp word pairs, one lane per chain
+    if (tid < 6 * (SMALL_W / 2)) {
+        const int t = tid >> 2, wp = tid & 3;
+        if (wp < nwp) {
+            unsigned long long *p = &S.b.tab[t][wp][0];
+            unsigned long long acc = 0ull;
+            if (t & 1) {
+#pragma unroll 8
+                for (int bnn = 0; bnn < NBIN; ++bnn) { acc |= p[bnn]; p[bnn] = acc; }
+            } else {
+#pragma unroll 8
+                for (int bnn = NBIN - 1; bnn >= 0; --bnn) { acc |= p[bnn]; p[bnn] = acc; }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- 4. candidate pairs (i < j) -> this warp's queue ----
+    unsigned qcount = 0u;
+    bool overflow = false;
+    {
+        unsigned short *myq = S.a.queue[warp];
+        const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+        for (int u = 0; u < SMALL_EPT; ++u) {
+            const int j0 = wbase + u * SMALL_THREADS;           // first row of this warp's block of 32 (warp-uniform)
+            if (j0 < n) {
+                const int j = j0 + lane;
+                const unsigned bn = (j < n) ? S.bins[j] : 0x80000000u;
+                const bool act = !(bn >> 31);
+                const int bx1 = bn & 63, bx2 = (bn >> 6) & 63, by1 = (bn >> 12) & 63, by2 = (bn >> 18) & 63, ab = (bn >> 24) & 63;
+                const int wpj = j0 >> 6;
+                for (int wp = 0; wp <= wpj; ++wp) {
+                    const unsigned long long ex = S.b.tab[0][wp][bx2] | S.b.tab[1][wp][bx1] | S.b.tab[2][wp][by2] |
+                                                  S.b.tab[3][wp][by1] | S.b.tab[4][wp][ab] | S.b.tab[5][wp][ab];
+                    const int rel = j - 64 * wp;                 // rows of this warp lie in one 64-block: rel >= 0
+                    const unsigned long long lim = (rel >= 64) ? ~0ull : ((1ull << rel) - 1ull);
+                    const unsigned long long cw = act ? (~ex & lim) : 0ull;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        unsigned c = h ? (unsigned)(cw >> 32) : (unsigned)cw;
+                        const int ibase = 64 * wp + 32 * h;
+                        while (__any_sync(FULL, c != 0u)) {
+                            const bool has = c != 0u;
+                            const unsigned m = __ballot_sync(FULL, has);
+                            if (has) {
+                                const int ii = __ffs(c) - 1;
+                                c &= c - 1u;
+                                const unsigned slot = qcount + __popc(m & lt);
+                                if (slot < (unsigned)QCAP_W) myq[slot] = (unsigned short)((j << 8) | (ibase + ii));
+                                else overflow = true;
+                            }
+                            qcount += __popc(m);
+                        }
+                    }
+                }
+            }
+        }
+        if (lane == 0) S.qn[warp] = min(qcount, (unsigned)QCAP_W);
+    }
+    if (__syncthreads_or(overflow)) {
+        // dense overlap graph: more candidate pairs than the queue holds -- the chunked big tier takes the segment
+        if (tid == 0) big_list[atomicAdd(big_count, 1u)] = (unsigned)seg;
+        return;
+    }
+    const unsigned qtotal = S.qn[0] + S.qn[1] + S.qn[2] + S.qn[3];
+
+    // ---- 5. exact tests on the queued pairs, suppression matrix, resolve ----
+    bool any_edges = false;
+    if (qtotal != 0u) {                                          // CTA-uniform
+        uint4 *z = reinterpret_cast<uint4 *>(&S.b.T[0][0]);
+        for (int i = tid; i < n * (SMALL_W / 4); i += SMALL_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+        __syncthreads();
+        bool found = false;
+#pragma unroll 1
+        for (int wq = 0; wq < SMALL_WARPS; ++wq) {
+            const unsigned cq = S.qn[wq];
+            for (unsigned q = tid; q < cq; q += SMALL_THREADS) {
+                const unsigned e = S.a.queue[wq][q];
+                const int j = e >> 8, i = e & 255;
+                const float4 bj = S.box[j], bi = S.box[i];
+                if (suppresses_pos(bj, box_area(bj), bi, box_area(bi), thr)) {
+                    atomicOr(&S.b.T[j][i >> 5], 1u << (i & 31));
+                    atomicOr(&S.dirty[j >> 5], 1u << (j & 31));
+                    found = true;
+                }
+            }
+        }
+        any_edges = __syncthreads_or(found) != 0;
+    }
+    if (tid < 32) {
+        // lane w owns kept word w; only rows with a suppressor are visited, in score order (utils.py:67-84)
+        unsigned keptw = 0u;
+        if (lane < nw) keptw = (lane == nw - 1 && (n & 31)) ? ((1u << (n & 31)) - 1u) : FULL;
+        if (any_edges) {
+            for (int w = 0; w < nw; ++w) {
+                unsigned d = S.dirty[w];
+                while (d) {
+                    const int jj = __ffs(d) - 1;
+                    d &= d - 1u;
+                    const unsigned t = (lane <= w) ? S.b.T[32 * w + jj][lane & (SMALL_W - 1)] : 0u;
+                    if (__any_sync(FULL, (t & keptw) != 0u) && lane == w) keptw &= ~(1u << jj);
+                }
+            }
+        }
+        int c = __popc(keptw), incl = c;
+#pragma unroll
+        for (int o = 1; o < SMALL_W; o <<= 1) {
+            const int v = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane < SMALL_W) { S.keptw[lane] = keptw; S.pref[lane] = (unsigned)(incl - c); }
+        if (lane == SMALL_W - 1) { S.pref[SMALL_W] = (unsigned)incl; kept_count[seg] = (unsigned)incl; }
+    }
+    __syncthreads();
+
+    // ---- 6. finished rows: stage in shared memory (the tables / T are dead), store as one contiguous run ----
+    const float fc = (float)(seg % C);                           // utils.py:183 class id stored as float
+    for (int j = tid; j < n; j += SMALL_THREADS) {
+        const unsigned kw = S.keptw[j >> 5];
+        if ((kw >> (j & 31)) & 1u) {
+            const unsigned q = S.pref[j >> 5] + __popc(kw & ((1u << (j & 31)) - 1u));
+            const uint2 co = S.co[j];
+            store_row(S.b.stage + q * 7, S.box[j], co.x, co.y, fc);
+        }
+    }
+    __syncthreads();
+    {
+        const int nf = (int)S.pref[SMALL_W] * 7;
+        float4 *dst4 = reinterpret_cast<float4 *>(rec);
+        const float4 *src4 = reinterpret_cast<const float4 *>(S.b.stage);
+        for (int i = tid; i < (nf >> 2); i += SMALL_THREADS) dst4[i] = src4[i];
+        const int tail = nf & ~3;
+        if (tid < (nf & 3)) reinterpret_cast<float *>(rec)[tail + tid] = S.b.stage[tail + tid];
+    }
+}
+
+// ---- big tier ---------------------------------------------------------------------------------------------
 struct SmemStore {
     unsigned long long *key;   // ascending sort key: (~score order bits) << 32 | ~row
-    unsigned *conf;
-    float4 *box;               // sanitised when POS
-    float *area;
-    __device__ __forceinline__ unsigned long long get_key(int i) const { return key[i]; }
+    unsigned short *idx;       // sorted position -> record index
+    const float4 *ubox;        // record order, original boxes
+    bool pos;
     __device__ __forceinline__ void cswap(int i, int j)
     {
         const unsigned long long a = key[i], b = key[j];
-        if (b < a) { key[i] = b; key[j] = a; const unsigned t = conf[i]; conf[i] = conf[j]; conf[j] = t; }
+        if (b < a) { key[i] = b; key[j] = a; const unsigned short t = idx[i]; idx[i] = idx[j]; idx[j] = t; }
     }
-    __device__ __forceinline__ float4 get_box(int i) const { return box[i]; }
-    __device__ __forceinline__ float get_area(int i) const { return area[i]; }
+    __device__ __forceinline__ float4 get_box(int i) const { const float4 b = ubox[idx[i]]; return pos ? sanitise(b) : b; }
+    __device__ __forceinline__ float get_area(int i) const { return box_area(ubox[idx[i]]); }
 };
 
 struct GlobalStore {
-    uint4 *rec;                // {key hi, key lo, conf, 0}
-    const float4 *boxes;       // boxtab + b*M
+    uint4 *rec;                // record i: rec[2i] = {key hi, key lo, conf, obj}, rec[2i+1] = box
     bool pos;
-    __device__ __forceinline__ unsigned long long get_key(int i) const
-    {
-        const uint4 r = rec[i];
-        return ((unsigned long long)r.x << 32) | r.y;
-    }
     __device__ __forceinline__ void cswap(int i, int j)
     {
-        const uint4 a = rec[i], b = rec[j];
+        const uint4 a = rec[2 * i], b = rec[2 * j];
         const unsigned long long ka = ((unsigned long long)a.x << 32) | a.y, kb = ((unsigned long long)b.x << 32) | b.y;
-        if (kb < ka) { rec[i] = b; rec[j] = a; }
+        if (kb < ka) {
+            const uint4 ab = rec[2 * i + 1], bb = rec[2 * j + 1];
+            rec[2 * i] = b; rec[2 * j] = a; rec[2 * i + 1] = bb; rec[2 * j + 1] = ab;
+        }
     }
     __device__ __forceinline__ float4 get_box(int i) const
     {
-        const float4 b = boxes[~rec[i].y];
+        const float4 b = as_float4(rec[2 * i + 1]);
         return pos ? sanitise(b) : b;
     }
-    __device__ __forceinline__ float get_area(int i) const { return box_area(boxes[~rec[i].y]); }
+    __device__ __forceinline__ float get_area(int i) const { return box_area(as_float4(rec[2 * i + 1])); }
 };
 
 // Bitonic network in the "flip" formulation: every compare-exchange orders ascending, so virtual +inf padding
@@ -197,377 +585,16 @@ __device__ int greedy_nms(Store &s, int n, float thr, unsigned short *kept_s, un
     return *sh_nk;
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// Small tier (the common case: ~150 candidates per (image,class) at conf 1e-4): everything in ~18 KB of shared memory.
-//   1. rank sort on the unique 64-bit key (each thread counts the keys below its own; broadcast reads, no barriers)
-//   2. transposed suppression matrix T[j] = { i < j : IoU(i,j) >= thr }, one row per thread, all pairs independent
-//   3. warp 0 walks j in score order: kept[j] = (T[j] & kept) == 0        (utils.py:67-84)
-// Segments with more than SMALL_R candidates are queued for the big tier.
-// ---------------------------------------------------------------------------------------------------------------
-constexpr int SMALL_R = 256;
-constexpr int SMALL_W = SMALL_R / 32;
-#ifndef YL_SMALL_THREADS
-#define YL_SMALL_THREADS 128
-#endif
-constexpr int SMALL_THREADS = YL_SMALL_THREADS;
-constexpr int SMALL_EPT = SMALL_R / SMALL_THREADS;      // records per thread, at most
-
-// Conservative 16-bit image of a (sanitised) box for the pair prefilter: corners are rounded outwards (floor for x1,y1,
-// ceil for x2,y2), clamped to +-16384 px and biased to 15-bit unsigned, two per 32-bit word.  Rounding and clamping are
-// monotone, so  true overlap (tl < br on both axes)  =>  q(tl) <= q(br) on both axes : the integer test never rejects
-// a pair the exact fp32 test would accept.  A NaN box (sanitised to +inf/-inf) maps to lo=32767 > hi=0: never overlaps.
-__device__ __forceinline__ uint2 quantise_box(const float4 &b)
-{
-    const int x1 = min(max(__float2int_rd(fminf(fmaxf(b.x, -16384.0f), 16383.0f)), -16384), 16383) + 16384;
-    const int y1 = min(max(__float2int_rd(fminf(fmaxf(b.y, -16384.0f), 16383.0f)), -16384), 16383) + 16384;
-    const int x2 = min(max(__float2int_ru(fminf(fmaxf(b.z, -16384.0f), 16383.0f)), -16384), 16383) + 16384;
-    const int y2 = min(max(__float2int_ru(fminf(fmaxf(b.w, -16384.0f), 16383.0f)), -16384), 16383) + 16384;
-    return make_uint2((unsigned)x1 | ((unsigned)y1 << 16), (unsigned)x2 | ((unsigned)y2 << 16));
-}
-
-// (br + 0x8000 - tl) per 16-bit half never borrows or overflows for 15-bit operands; bit 15 of a half is set iff br >= tl.
-__device__ __forceinline__ bool may_overlap(const uint2 &a, const uint2 &b)
-{
-    const unsigned tl = __vmaxu2(a.x, b.x), br = __vminu2(a.y, b.y);
-    return ((br + 0x80008000u - tl) & 0x80008000u) == 0x80008000u;
-}
-
-// Row j of the transposed suppression matrix: bit i (i < j) set when box i suppresses box j.
-// Number of keys below `key` (keys are unique): LDS.128 per two keys, one 64-bit compare + predicated add per key.
-__device__ __forceinline__ int rank_of(const unsigned long long *sh_key, int n, unsigned long long key)
-{
-    int r = 0;
-    const ulonglong2 *k2 = reinterpret_cast<const ulonglong2 *>(sh_key);
-    const int n2 = (n + 1) >> 1;
-#pragma unroll 4
-    for (int j = 0; j < n2; ++j) {
-        const ulonglong2 k = k2[j];
-        asm("{\n\t.reg .pred p, q;\n\tsetp.lt.u64 p, %1, %3;\n\tsetp.lt.u64 q, %2, %3;\n\t@p add.s32 %0, %0, 1;\n\t@q add.s32 %0, %0, 1;\n\t}"
-            : "+r"(r) : "l"(k.x), "l"(k.y), "l"(key));
-    }
-    return r;
-}
-
-template <bool POS>
-__device__ __forceinline__ void small_pairs(const float4 *sh_box, const float *sh_area, const uint2 *sh_q,
-                                            unsigned (*sh_T)[SMALL_W + 1], int n, float thr)
-{
-    for (int j0 = 0; j0 < n; j0 += SMALL_THREADS) {
-        const int j = j0 + (int)threadIdx.x;
-        const int jw = (j0 + ((int)threadIdx.x & ~31)) >> 5;        // word of this warp's rows (warp-uniform)
-        if (32 * jw >= n) break;                                     // the whole warp is past the segment
-        const bool have = j < n;
-        const float4 bj = sh_box[have ? j : 0];
-        const float aj = sh_area[have ? j : 0];
-        const uint2 qj = sh_q[have ? j : 0];
-        for (int w = 0; w <= jw; ++w) {
-            unsigned word = 0u;
-            const unsigned lim_mask = (w < jw) ? 0xFFFFFFFFu : ((1u << (j & 31)) - 1u);      // diagonal block: only i < j
-            if (POS) {
-                // branch-free integer prefilter over the 32 boxes of the block, then the exact test on the few survivors
-                unsigned cand = 0u;
-#pragma unroll
-                for (int ii = 0; ii < 32; ++ii) cand |= may_overlap(qj, sh_q[32 * w + ii]) ? (1u << ii) : 0u;
-                cand &= lim_mask;
-                while (cand) {
-                    const int ii = __ffs(cand) - 1;
-                    cand &= cand - 1;
-                    const int i = 32 * w + ii;
-                    if (suppresses_pos(bj, aj, sh_box[i], sh_area[i], thr)) word |= 1u << ii;
-                }
-            } else {
-#pragma unroll 4
-                for (int ii = 0; ii < 32; ++ii) {
-                    const int i = 32 * w + ii;
-                    if (((lim_mask >> ii) & 1u) && suppresses_any(bj, aj, sh_box[i], sh_area[i], thr)) word |= 1u << ii;
-                }
-            }
-            if (have) sh_T[j][w] = word;
-        }
-    }
-}
-
-__global__ void __launch_bounds__(SMALL_THREADS)
-k_segment_nms_small(uint4 *__restrict__ cand, const unsigned *__restrict__ seg_count, unsigned *__restrict__ kept_count,
-                    const float4 *__restrict__ boxtab, long M, int C, int cap_seg, float thr, int seg_first,
-                    unsigned *__restrict__ big_count, unsigned *__restrict__ big_list)
-{
-    __shared__ __align__(16) unsigned long long sh_key[SMALL_R + 2];
-    __shared__ unsigned sh_row[SMALL_R], sh_conf[SMALL_R];      // sorted
-    __shared__ float4 sh_box[SMALL_R];
-    __shared__ float sh_area[SMALL_R];
-    __shared__ uint2 sh_q[SMALL_R];                             // 16-bit conservative corners for the pair prefilter
-    __shared__ unsigned sh_T[SMALL_R][SMALL_W + 1];             // +1: conflict-free row writes
-    __shared__ unsigned sh_kw[SMALL_W], sh_pref[SMALL_W + 1];
-
-    const int seg = seg_first + blockIdx.x;
-    const unsigned cnt = seg_count[seg];
-    if (cnt == 0u) return;                                      // kept_count was zeroed by yl_post_reset
-    if (cnt > (unsigned)cap_seg) return;                        // overflow: reported through meta[], caller re-runs
-    const int tid = threadIdx.x;
-    if (cnt > (unsigned)SMALL_R) {
-        if (tid == 0) big_list[atomicAdd(big_count, 1u)] = (unsigned)seg;
-        return;
-    }
-    const int n = (int)cnt;
-    const int b = seg / C;
-    uint4 *rec = cand + (size_t)seg * cap_seg;
-    const float4 *boxes = boxtab + (size_t)b * M;
-    const bool pos = thr > 0.0f;
-
-    // load (at most two records per thread), start the box gathers, then rank
-    unsigned long long key[SMALL_EPT];
-    unsigned conf[SMALL_EPT], row[SMALL_EPT];
-    float4 bx[SMALL_EPT];
-#pragma unroll
-    for (int u = 0; u < SMALL_EPT; ++u) {
-        const int i = tid + u * SMALL_THREADS;
-        key[u] = ~0ull; conf[u] = 0u; row[u] = 0u;
-        if (i < n) {
-            const uint4 r = rec[i];
-            key[u] = ((unsigned long long)score_desc_bits(r.x) << 32) | (unsigned)(~r.y);
-            conf[u] = r.z; row[u] = r.y;
-            sh_key[i] = key[u];
-        }
-    }
-#pragma unroll
-    for (int u = 0; u < SMALL_EPT; ++u)
-        if (tid + u * SMALL_THREADS < n) bx[u] = boxes[row[u]];
-    __syncthreads();
-    int rank[SMALL_EPT];
-#pragma unroll
-    for (int u = 0; u < SMALL_EPT; ++u) rank[u] = 0;
-    const int wbase = tid & ~31;                                // first element index of this warp (warp-uniform bounds below)
-    // keys beyond n were never written: pad the tail of the last 16-byte pair so the 2-wide loop may read it
-    if (tid == 0 && (n & 1)) sh_key[n] = ~0ull;
-    __syncthreads();
-#pragma unroll
-    for (int u = 0; u < SMALL_EPT; ++u)
-        if (wbase + u * SMALL_THREADS < n) rank[u] = rank_of(sh_key, n, key[u]);          // warp-uniform bound
-#pragma unroll
-    for (int u = 0; u < SMALL_EPT; ++u)
-        if (tid + u * SMALL_THREADS < n) {
-            const int r = rank[u];
-            sh_row[r] = row[u]; sh_conf[r] = conf[u];
-            sh_area[r] = box_area(bx[u]);
-            const float4 sb = pos ? sanitise(bx[u]) : bx[u];
-            sh_box[r] = sb;
-            sh_q[r] = quantise_box(sb);
-        }
-    __syncthreads();
-    if (pos) small_pairs<true>(sh_box, sh_area, sh_q, sh_T, n, thr);
-    else small_pairs<false>(sh_box, sh_area, sh_q, sh_T, n, thr);
-    __syncthreads();
-    if (tid < 32) {
-        unsigned keptw = 0u;                                    // lane w owns kept word w
-        const int lw = tid < SMALL_W ? tid : 0;
-        int j = 0;
-        // row j only has words 0..j/32 (the rest was never written): lanes above the diagonal contribute nothing
-        for (; j + 4 <= n; j += 4) {
-            const bool rd = tid <= (j >> 5);                    // j..j+3 share j>>5 (j is a multiple of 4)
-            const unsigned t0 = rd ? sh_T[j][lw] : 0u, t1 = rd ? sh_T[j + 1][lw] : 0u;
-            const unsigned t2 = rd ? sh_T[j + 2][lw] : 0u, t3 = rd ? sh_T[j + 3][lw] : 0u;
-            if (!__any_sync(0xFFFFFFFFu, t0 & keptw) && tid == (j >> 5)) keptw |= 1u << (j & 31);
-            if (!__any_sync(0xFFFFFFFFu, t1 & keptw) && tid == (j >> 5)) keptw |= 1u << ((j + 1) & 31);
-            if (!__any_sync(0xFFFFFFFFu, t2 & keptw) && tid == (j >> 5)) keptw |= 1u << ((j + 2) & 31);
-            if (!__any_sync(0xFFFFFFFFu, t3 & keptw) && tid == (j >> 5)) keptw |= 1u << ((j + 3) & 31);
-        }
-        for (; j < n; ++j) {
-            const unsigned t0 = (tid <= (j >> 5)) ? sh_T[j][lw] : 0u;
-            if (!__any_sync(0xFFFFFFFFu, t0 & keptw) && tid == (j >> 5)) keptw |= 1u << (j & 31);
-        }
-        int c = (tid < SMALL_W) ? __popc(keptw) : 0, incl = c;
-#pragma unroll
-        for (int o = 1; o < SMALL_W; o <<= 1) {
-            const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-            if (tid >= o) incl += v;
-        }
-        if (tid < SMALL_W) { sh_kw[tid] = keptw; sh_pref[tid] = (unsigned)(incl - c); }
-        if (tid == SMALL_W - 1) { sh_pref[SMALL_W] = (unsigned)incl; kept_count[seg] = (unsigned)incl; }
-    }
-    __syncthreads();
-    for (int j2 = tid; j2 < n; j2 += SMALL_THREADS) {
-        const unsigned kw = sh_kw[j2 >> 5];
-        if ((kw >> (j2 & 31)) & 1u) {
-            const unsigned q = sh_pref[j2 >> 5] + __popc(kw & ((1u << (j2 & 31)) - 1u));
-            rec[q] = make_uint4(sh_row[j2], sh_conf[j2], 0u, 0u);        // {box row, cls_conf bits}
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// Small tier, warp-per-segment form (default): one warp owns one (image,class) segment end to end, so there are no
-// block barriers and no warp ever idles while another resolves; a CTA is just WS_WARPS independent segments.
-//   1. records -> shared memory (key, row, conf) + box gather; 2. rank sort on the unique key;
-//   3. sorted conservative corners q[] + permutation;  4. per block of 32 sorted candidates: integer prefilter against
-//   every kept earlier box (exact fp32 test only on prefilter hits), 32x32 diagonal block, serial resolve by ballot,
-//   kept records appended in score order.
-// ---------------------------------------------------------------------------------------------------------------
-constexpr int WS_WARPS = 4;
-constexpr int WS_U = SMALL_R / 32;         // records per lane, at most
-
-struct alignas(16) WsSeg {
-    union {
-        unsigned long long key[SMALL_R + 2];   // while ranking
-        uint2 q[SMALL_R];                      // afterwards: conservative 16-bit corners in sorted order
-    };
-    float4 ubox[SMALL_R];                      // record order; sanitised when thr > 0
-    unsigned urow[SMALL_R], uconf[SMALL_R];    // record order
-    unsigned short perm[SMALL_R];              // sorted position -> record index
-};
-
-template <bool POS>
-__device__ __forceinline__ void warp_segment_nms(WsSeg &S, uint4 *__restrict__ rec, const float4 *__restrict__ boxes, int n,
-                                                 float thr, unsigned *kept_count_out)
-{
-    const unsigned FULL = 0xFFFFFFFFu;
-    const int lane = threadIdx.x & 31;
-    const int nu = (n + 31) >> 5;
-    unsigned long long mykey[WS_U];
-    // 1. records, then boxes (all loads of a phase in flight together)
-    {
-        uint4 r[WS_U];
-#pragma unroll
-        for (int u = 0; u < WS_U; ++u)
-            if (u < nu) { const int e = lane + 32 * u; r[u] = (e < n) ? rec[e] : make_uint4(0u, 0u, 0u, 0u); }
-        float4 bx[WS_U];
-#pragma unroll
-        for (int u = 0; u < WS_U; ++u)
-            if (u < nu) { const int e = lane + 32 * u; if (e < n) bx[u] = boxes[r[u].y]; }
-#pragma unroll
-        for (int u = 0; u < WS_U; ++u) {
-            mykey[u] = ~0ull;
-            if (u < nu) {
-                const int e = lane + 32 * u;
-                if (e < n) {
-                    mykey[u] = ((unsigned long long)score_desc_bits(r[u].x) << 32) | (unsigned)(~r[u].y);
-                    S.key[e] = mykey[u];
-                    S.urow[e] = r[u].y; S.uconf[e] = r[u].z;
-                    S.ubox[e] = POS ? sanitise(bx[u]) : bx[u];
-                }
-            }
-        }
-        if (lane == 0 && (n & 1)) S.key[n] = ~0ull;              // rank_of reads keys two at a time
-    }
-    __syncwarp();
-    // 2. rank
-    int rank[WS_U];
-#pragma unroll
-    for (int u = 0; u < WS_U; ++u) rank[u] = (u < nu) ? rank_of(S.key, n, mykey[u]) : 0;
-    __syncwarp();                                                // key storage is reused below
-    // 3. sorted prefilter corners + permutation
-#pragma unroll
-    for (int u = 0; u < WS_U; ++u)
-        if (u < nu) {
-            const int e = lane + 32 * u;
-            if (e < n) { S.q[rank[u]] = quantise_box(S.ubox[e]); S.perm[rank[u]] = (unsigned short)e; }
-        }
-    __syncwarp();
-    // 4. blocks of 32 in score order
-    unsigned keptw = 0u;                                         // lane w owns the kept bits of block w
-    int nk = 0;
-    for (int jb = 0; jb < nu; ++jb) {
-        const int j = 32 * jb + lane;
-        const bool have = j < n;
-        const int ej = have ? (int)S.perm[j] : 0;
-        const uint2 qj = have ? S.q[j] : make_uint2(0x7FFF7FFFu, 0u);
-        const float4 bj = S.ubox[ej];
-        const float aj = box_area(bj);
-        bool supp = false;
-        for (int ib = 0; ib < jb; ++ib) {
-            const unsigned kw = __shfl_sync(FULL, keptw, ib);
-            if (kw == 0u) continue;                              // warp-uniform
-            unsigned cand;
-            if (POS) {
-                cand = 0u;
-#pragma unroll
-                for (int ii = 0; ii < 32; ++ii) cand |= may_overlap(qj, S.q[32 * ib + ii]) ? (1u << ii) : 0u;
-                cand &= kw;
-            } else {
-                cand = kw;
-            }
-            if (!have || supp) cand = 0u;
-            while (cand) {
-                const int ii = __ffs(cand) - 1;
-                cand &= cand - 1;
-                const float4 bi = S.ubox[S.perm[32 * ib + ii]];
-                const bool sup = POS ? suppresses_pos(bj, aj, bi, box_area(bi), thr) : suppresses_any(bj, aj, bi, box_area(bi), thr);
-                if (sup) { supp = true; cand = 0u; }
-            }
-        }
-        // diagonal block: candidates i < j of the same block
-        const int nvalid = min(32, n - 32 * jb);
-        unsigned cand;
-        if (POS) {
-            cand = 0u;
-#pragma unroll
-            for (int ii = 0; ii < 32; ++ii) cand |= may_overlap(qj, S.q[32 * jb + ii]) ? (1u << ii) : 0u;
-        } else {
-            cand = FULL;
-        }
-        cand &= ((1u << lane) - 1u) & (nvalid == 32 ? FULL : ((1u << nvalid) - 1u));
-        if (!have || supp) cand = 0u;
-        unsigned word = 0u;
-        while (cand) {
-            const int ii = __ffs(cand) - 1;
-            cand &= cand - 1;
-            const float4 bi = S.ubox[S.perm[32 * jb + ii]];
-            const bool sup = POS ? suppresses_pos(bj, aj, bi, box_area(bi), thr) : suppresses_any(bj, aj, bi, box_area(bi), thr);
-            word |= sup ? (1u << ii) : 0u;
-        }
-        unsigned removed = __ballot_sync(FULL, supp || !have);
-        unsigned keep;
-        if (!__any_sync(FULL, word != 0u)) {
-            keep = ~removed;                                     // nothing inside the block suppresses anything
-        } else {
-            keep = 0u;
-            for (int i = 0; i < nvalid; ++i) {                   // warp-uniform serial resolve (utils.py:67-84)
-                const unsigned hit = __ballot_sync(FULL, (word >> i) & 1u);   // lanes that box i suppresses
-                if (!((removed >> i) & 1u)) { keep |= 1u << i; removed |= hit; }
-            }
-        }
-        if (lane == jb) keptw = keep;
-        if ((keep >> lane) & 1u) rec[nk + __popc(keep & ((1u << lane) - 1u))] = make_uint4(S.urow[ej], S.uconf[ej], 0u, 0u);
-        nk += __popc(keep);
-    }
-    if (lane == 0) *kept_count_out = (unsigned)nk;
-    __syncwarp();
-}
-
-__global__ void __launch_bounds__(WS_WARPS * 32)
-k_segment_nms_warp(uint4 *__restrict__ cand, const unsigned *__restrict__ seg_count, unsigned *__restrict__ kept_count,
-                   const float4 *__restrict__ boxtab, long M, int C, int cap_seg, float thr, int seg_first, int nseg,
-                   unsigned *__restrict__ big_count, unsigned *__restrict__ big_list)
-{
-    __shared__ WsSeg sh[WS_WARPS];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int sl = blockIdx.x * WS_WARPS + warp;
-    if (sl >= nseg) return;
-    const int seg = seg_first + sl;
-    const unsigned cnt = seg_count[seg];
-    if (cnt == 0u) return;                                      // kept_count was zeroed by yl_post_reset
-    if (cnt > (unsigned)cap_seg) return;                        // overflow: reported through meta[], caller re-runs
-    if (cnt > (unsigned)SMALL_R) {
-        if (lane == 0) big_list[atomicAdd(big_count, 1u)] = (unsigned)seg;
-        return;
-    }
-    uint4 *rec = cand + (size_t)seg * cap_seg;
-    const float4 *boxes = boxtab + (size_t)(seg / C) * M;
-    if (thr > 0.0f) warp_segment_nms<true>(sh[warp], rec, boxes, (int)cnt, thr, &kept_count[seg]);
-    else warp_segment_nms<false>(sh[warp], rec, boxes, (int)cnt, thr, &kept_count[seg]);
-}
-
-// Big tier: persistent CTAs walk the list of segments the small tier could not take (more than SMALL_R candidates).
+// Persistent CTAs walk the list of segments the small tier passed on.
 __global__ void __launch_bounds__(NMS_THREADS)
 k_segment_nms_big(uint4 *__restrict__ cand, const unsigned *__restrict__ seg_count, unsigned *__restrict__ kept_count,
-                  const float4 *__restrict__ boxtab, long M, int C, int cap_seg, float thr,
-                  const unsigned *__restrict__ big_count, const unsigned *__restrict__ big_list,
+                  int C, int cap_seg, float thr, const unsigned *__restrict__ big_count, const unsigned *__restrict__ big_list,
                   unsigned *__restrict__ kept_scratch /* [B*C*cap_seg] u32, only when cap_seg > SMEM_R; else null */)
 {
     __shared__ unsigned long long sh_key[SMEM_R];
-    __shared__ unsigned sh_conf[SMEM_R];
-    __shared__ float4 sh_box[SMEM_R];
-    __shared__ float sh_area[SMEM_R];
+    __shared__ unsigned short sh_idx[SMEM_R];
+    __shared__ float4 sh_ubox[SMEM_R];
+    __shared__ uint2 sh_uco[SMEM_R];
     __shared__ unsigned short sh_kept[SMEM_R];
     __shared__ unsigned long long sh_rows[CHUNK];
     __shared__ unsigned sh_supp[2];
@@ -575,70 +602,67 @@ k_segment_nms_big(uint4 *__restrict__ cand, const unsigned *__restrict__ seg_cou
 
     const unsigned nbig = *big_count;
     for (unsigned it = blockIdx.x; it < nbig; it += gridDim.x) {
-    const int seg = (int)big_list[it];
-    const int b = seg / C;
-    const unsigned cnt = seg_count[seg];
-    const int n = (int)cnt;
-    uint4 *rec = cand + (size_t)seg * cap_seg;
-    const float4 *boxes = boxtab + (size_t)b * M;
-    const int tid = threadIdx.x;
-    const bool pos = thr > 0.0f;
+        const int seg = (int)big_list[it];
+        const int n = (int)seg_count[seg];
+        uint4 *rec = cand + (size_t)seg * cap_seg * 2;
+        float *rows = reinterpret_cast<float *>(rec);
+        const float fc = (float)(seg % C);
+        const int tid = threadIdx.x;
+        const bool pos = thr > 0.0f;
 
-    if (n <= SMEM_R) {
-        for (int i = tid; i < n; i += NMS_THREADS) {
-            const uint4 r = rec[i];
-            sh_key[i] = ((unsigned long long)score_desc_bits(r.x) << 32) | (unsigned)(~r.y);
-            sh_conf[i] = r.z;
-        }
-        __syncthreads();
-        SmemStore s{sh_key, sh_conf, sh_box, sh_area};
-        bitonic_sort(s, n);
-        for (int i = tid; i < n; i += NMS_THREADS) {
-            const float4 bx = boxes[~(unsigned)sh_key[i]];
-            sh_area[i] = box_area(bx);
-            sh_box[i] = pos ? sanitise(bx) : bx;
-        }
-        __syncthreads();
-        const int nk = pos ? greedy_nms<true>(s, n, thr, sh_kept, nullptr, sh_supp, sh_rows, &sh_nk)
-                           : greedy_nms<false>(s, n, thr, sh_kept, nullptr, sh_supp, sh_rows, &sh_nk);
-        for (int q = tid; q < nk; q += NMS_THREADS) {
-            const int i = sh_kept[q];
-            rec[q] = make_uint4(~(unsigned)sh_key[i], sh_conf[i], 0u, 0u);      // {box row, cls_conf bits}
-        }
-        if (tid == 0) kept_count[seg] = (unsigned)nk;
-    } else {
-        // oversized segment: same algorithm in place in global memory (slow path, correctness only)
-        for (int i = tid; i < n; i += NMS_THREADS) {
-            const uint4 r = rec[i];
-            rec[i] = make_uint4(score_desc_bits(r.x), ~r.y, r.z, 0u);
-        }
-        __syncthreads();
-        GlobalStore s{rec, boxes, pos};
-        bitonic_sort(s, n);
-        unsigned *kept_g = kept_scratch + (size_t)seg * cap_seg;
-        const int nk = pos ? greedy_nms<true>(s, n, thr, nullptr, kept_g, sh_supp, sh_rows, &sh_nk)
-                           : greedy_nms<false>(s, n, thr, nullptr, kept_g, sh_supp, sh_rows, &sh_nk);
-        // compact in place: kept_g[q] >= q and strictly increasing, so go through registers chunk by chunk
-        for (int q0 = 0; q0 < nk; q0 += NMS_THREADS) {
-            const int q = q0 + tid;
-            uint4 r = make_uint4(0, 0, 0, 0);
-            if (q < nk) r = rec[kept_g[q]];
+        if (n <= SMEM_R) {
+            for (int i = tid; i < n; i += NMS_THREADS) {
+                const uint4 a = rec[2 * i];
+                sh_key[i] = ((unsigned long long)score_desc_bits(a.x) << 32) | (unsigned)(~a.y);
+                sh_idx[i] = (unsigned short)i;
+                sh_uco[i] = make_uint2(a.z, a.w);
+                sh_ubox[i] = as_float4(rec[2 * i + 1]);
+            }
             __syncthreads();
-            if (q < nk) rec[q] = make_uint4(~r.y, r.z, 0u, 0u);
+            SmemStore s{sh_key, sh_idx, sh_ubox, pos};
+            bitonic_sort(s, n);
+            const int nk = pos ? greedy_nms<true>(s, n, thr, sh_kept, nullptr, sh_supp, sh_rows, &sh_nk)
+                               : greedy_nms<false>(s, n, thr, sh_kept, nullptr, sh_supp, sh_rows, &sh_nk);
+            for (int q = tid; q < nk; q += NMS_THREADS) {
+                const int e = sh_idx[sh_kept[q]];
+                const uint2 co = sh_uco[e];
+                store_row(rows + (size_t)q * 7, sh_ubox[e], co.x, co.y, fc);
+            }
+            if (tid == 0) kept_count[seg] = (unsigned)nk;
+        } else {
+            // oversized segment: same algorithm in place in global memory (slow path, correctness only)
+            for (int i = tid; i < n; i += NMS_THREADS) {
+                const uint4 a = rec[2 * i];
+                rec[2 * i] = make_uint4(score_desc_bits(a.x), ~a.y, a.z, a.w);
+            }
             __syncthreads();
+            GlobalStore s{rec, pos};
+            bitonic_sort(s, n);
+            unsigned *kept_g = kept_scratch + (size_t)seg * cap_seg;
+            const int nk = pos ? greedy_nms<true>(s, n, thr, nullptr, kept_g, sh_supp, sh_rows, &sh_nk)
+                               : greedy_nms<false>(s, n, thr, nullptr, kept_g, sh_supp, sh_rows, &sh_nk);
+            // rows replace records in place: kept_g[q] >= q and a row (28 B) is shorter than a record (32 B), so the
+            // rows of a chunk never reach a record a later chunk still has to read; go through registers chunk by chunk
+            for (int q0 = 0; q0 < nk; q0 += NMS_THREADS) {
+                const int q = q0 + tid;
+                uint4 a = make_uint4(0u, 0u, 0u, 0u), bb = make_uint4(0u, 0u, 0u, 0u);
+                if (q < nk) { a = rec[2 * (size_t)kept_g[q]]; bb = rec[2 * (size_t)kept_g[q] + 1]; }
+                __syncthreads();
+                if (q < nk) store_row(rows + (size_t)q * 7, as_float4(bb), a.z, a.w, fc);
+                __syncthreads();
+            }
+            if (tid == 0) kept_count[seg] = (unsigned)nk;
         }
-        if (tid == 0) kept_count[seg] = (unsigned)nk;
-    }
-    __syncthreads();
+        __syncthreads();
     }
 }
 
 constexpr int GATHER_THREADS = 128;
 
+// The kept rows of a segment are finished and contiguous at the front of the segment: concatenation is a copy.
 __global__ void __launch_bounds__(GATHER_THREADS)
 k_gather_rows(const uint4 *__restrict__ cand, const unsigned *__restrict__ seg_count, const unsigned *__restrict__ kept_count,
-              const float4 *__restrict__ boxtab, const float *__restrict__ objtab, long M, int C, int cap_seg, int B,
-              float *__restrict__ out_rows, long cap_out, int *__restrict__ meta, int seg_first)
+              int C, int cap_seg, int B, float *__restrict__ out_rows, long cap_out, int *__restrict__ meta, int seg_first)
 {
     __shared__ unsigned sh_red[3][GATHER_THREADS / 32];
     const int seg = seg_first + blockIdx.x;
@@ -666,28 +690,30 @@ k_gather_rows(const uint4 *__restrict__ cand, const unsigned *__restrict__ seg_c
         if (c == C - 1) meta[b] = (int)(pre + nk);
         if (c == 0) { meta[B + b] = (int)mx; meta[2 * B + b] = (int)tot; }
     }
-    const uint4 *rec = cand + (size_t)seg * cap_seg;
-    const float fc = (float)c;                                             // utils.py:183 class id stored as float
-    // rows of a segment are consecutive in the output: gather 128 rows into shared memory, then store them as one
-    // contiguous run of 896 floats (coalesced) instead of seven 28-byte-strided scalar stores per thread
-    __shared__ float sh_rows[GATHER_THREADS * 7];
     const unsigned nwr = (unsigned)min((long)nk, max(0L, cap_out - (long)pre));      // rows that fit the output capacity
-    for (unsigned q0 = 0; q0 < nwr; q0 += GATHER_THREADS) {
-        const unsigned q = q0 + tid;
-        if (q < nwr) {
-            const uint4 e = rec[q];
-            const size_t brow = (size_t)b * M + e.x;
-            const float4 bx = boxtab[brow];
-            float *o = sh_rows + tid * 7;
-            o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w;
-            o[4] = objtab[brow]; o[5] = __uint_as_float(e.y); o[6] = fc;
+    const float *src = reinterpret_cast<const float *>(cand + (size_t)seg * cap_seg * 2);
+    float *dst = out_rows + ((size_t)b * cap_out + pre) * 7;
+    for (unsigned i = tid; i < nwr * 7u; i += GATHER_THREADS) dst[i] = src[i];
+}
+
+// Smallest K such that two positive areas whose bins (float bits >> 21: four per octave) differ by at least K have a
+// ratio above 1/(0.999 thr) * (1 + 1e-3): then IoU <= amin/amax < thr with a margin far above fp32 rounding, which is
+// the condition under which suppresses_pos returns false on the area test alone.
+static int area_bin_gap(float thr)
+{
+    if (!(thr > 0.0f)) return NBIN + 1;
+    const double need = 1.0 / (0.999 * (double)thr) * 1.001;
+    for (int K = 1; K <= NBIN; ++K) {
+        double worst = 1e300;
+        for (int p = 0; p < 4; ++p) {
+            // bins p+1 .. : lower edge of bin (p + K) over upper edge of bin p (= lower edge of bin p + 1)
+            const int hi = p + K, lo = p + 1;
+            const double Lh = ldexp(1.0 + (hi & 3) * 0.25, hi >> 2), Ll = ldexp(1.0 + (lo & 3) * 0.25, lo >> 2);
+            worst = fmin(worst, Lh / Ll);
         }
-        __syncthreads();
-        const unsigned nrun = min((unsigned)GATHER_THREADS, nwr - q0) * 7u;
-        float *dst = out_rows + ((size_t)b * cap_out + pre + q0) * 7;
-        for (unsigned i = tid; i < nrun; i += GATHER_THREADS) dst[i] = sh_rows[i];
-        __syncthreads();
+        if (worst >= need) return K;
     }
+    return NBIN + 1;
 }
 
 }  // namespace yl
@@ -707,29 +733,19 @@ extern "C" int yl_nms(void *ws, size_t ws_bytes, int B, long M, int C, int cap_s
     uint4 *cand = (uint4 *)(w + L.off_cand);
     unsigned *seg_count = (unsigned *)(w + L.off_seg_count);
     unsigned *kept_count = (unsigned *)(w + L.off_kept_count);
-    const float4 *boxtab = (const float4 *)(w + L.off_box);
-    const float *objtab = (const float *)(w + L.off_obj);
     unsigned *kept_scratch = (cap_seg > SMEM_R) ? (unsigned *)(w + L.off_kept_scratch) : nullptr;
     const int nseg = img_count * C, seg_first = img_first * C;
     unsigned *big_count = (unsigned *)(w + L.off_big_count) + img_first;
     unsigned *big_list = (unsigned *)(w + L.off_big_list) + seg_first;
-    // block-per-segment form by default (118 us vs 131 us at B=64, conf 1e-4); YL_NMS_WARP=1 selects warp-per-segment
-    static const bool cta_tier = !(getenv("YL_NMS_WARP") && getenv("YL_NMS_WARP")[0] == '1');
-    if (cta_tier)
-        k_segment_nms_small<<<nseg, SMALL_THREADS, 0, (cudaStream_t)stream>>>(cand, seg_count, kept_count, boxtab, L.M4, C, cap_seg,
-                                                                            nms_thre, seg_first, big_count, big_list);
-    else
-        k_segment_nms_warp<<<(nseg + WS_WARPS - 1) / WS_WARPS, WS_WARPS * 32, 0, (cudaStream_t)stream>>>(
-            cand, seg_count, kept_count, boxtab, L.M4, C, cap_seg, nms_thre, seg_first, nseg, big_count, big_list);
+    cudaStream_t st = (cudaStream_t)stream;
+    k_segment_nms_bins<<<nseg, SMALL_THREADS, 0, st>>>(cand, seg_count, kept_count, C, cap_seg, nms_thre, area_bin_gap(nms_thre),
+                                                      seg_first, big_count, big_list);
     YL_LAUNCH_CHECK();
-    if (cap_seg > SMALL_R) {
-        const int grid_big = nseg < 148 * 2 ? nseg : 148 * 2;
-        k_segment_nms_big<<<grid_big, NMS_THREADS, 0, (cudaStream_t)stream>>>(cand, seg_count, kept_count, boxtab, L.M4, C, cap_seg,
-                                                                             nms_thre, big_count, big_list, kept_scratch);
-        YL_LAUNCH_CHECK();
-    }
-    k_gather_rows<<<nseg, GATHER_THREADS, 0, (cudaStream_t)stream>>>(cand, seg_count, kept_count, boxtab, objtab, L.M4, C,
-                                                                   cap_seg, B, out_rows, cap_out, meta, seg_first);
+    const int grid_big = nseg < 148 * 2 ? nseg : 148 * 2;
+    k_segment_nms_big<<<grid_big, NMS_THREADS, 0, st>>>(cand, seg_count, kept_count, C, cap_seg, nms_thre, big_count, big_list,
+                                                       kept_scratch);
+    YL_LAUNCH_CHECK();
+    k_gather_rows<<<nseg, GATHER_THREADS, 0, st>>>(cand, seg_count, kept_count, C, cap_seg, B, out_rows, cap_out, meta, seg_first);
     YL_LAUNCH_CHECK();
     return YL_OK;
 }
