@@ -72,13 +72,12 @@ struct EmitWarp {
     unsigned short ent[K1_QCAP];       // bit15 pass | box slot (7b) << 8 | class (7b)
     unsigned cls[K1_QCAP];             // sigmoid(class logit) bits of passing entries
     unsigned any[4], nan[4];           // per box slot: has a surviving pair / has a NaN class logit
+    unsigned flg[4];                   // per box slot: belongs to the batch being resolved (speculative box fetch)
     float4 box[128];                   // decoded corners of the box slots that have a surviving pair
 };
 
-// Decode one box (yololayer.py:150-162) and convert to corners (utils.py:117-126).
-__device__ __forceinline__ float4 decode_box(const float *bp, int F2, int Fw, int p, float aw, float ah, float stride)
+__device__ __forceinline__ float4 decode_box_v(float tx, float ty, float tw, float th, int Fw, int p, float aw, float ah, float stride)
 {
-    const float tx = bp[0], ty = bp[(size_t)F2], tw = bp[2 * (size_t)F2], th = bp[3 * (size_t)F2];
     const int gy = p / Fw, gx = p - gy * Fw;
     const float bx = __fmul_rn(__fadd_rn(spec_sigmoidf(tx), (float)gx), stride);
     const float by = __fmul_rn(__fadd_rn(spec_sigmoidf(ty), (float)gy), stride);
@@ -88,11 +87,32 @@ __device__ __forceinline__ float4 decode_box(const float *bp, int F2, int Fw, in
     return make_float4(__fsub_rn(bx, hw), __fsub_rn(by, hh), __fadd_rn(bx, hw), __fadd_rn(by, hh));
 }
 
+// Decode one box (yololayer.py:150-162) and convert to corners (utils.py:117-126).
+__device__ __forceinline__ float4 decode_box(const float *bp, int F2, int Fw, int p, float aw, float ah, float stride)
+{
+    const float tx = bp[0], ty = bp[(size_t)F2], tw = bp[2 * (size_t)F2], th = bp[3 * (size_t)F2];
+    return decode_box_v(tx, ty, tw, th, Fw, p, aw, ah, stride);
+}
+
 // Exact pass over one batch of `total` queued (box slot, class) pairs of a warp tile.  All lanes take part:
-//   1. reload the flagged logits (all loads of a 128-entry round in flight together), exact spec-math test
-//   2. boxes with a surviving pair and no NaN class logit are decoded once (lane i takes the i-th such box)
-//   3. one record per surviving pair is appended to its (image, class) segment
-// sobj[slot] = sigmoid(objectness) of the warp tile's boxes; wbase = plane 0 of the (image, anchor) at the tile's first box.
+//   1. the box planes of the batch's boxes are requested speculatively (lane i takes the i-th flagged box slot; the
+//      conservative flag is tight, >95 % of flagged boxes survive) together with
+//   2. the flagged logits (all loads of a 128-entry round in flight), then the exact spec-math test;
+//   3. boxes with a surviving pair and no NaN class logit are decoded once, from the registers of step 1;
+//   4. one 32-byte record per surviving pair is appended to its (image, class) segment: the slot atomics of four
+//      entries per lane are issued before the first record is stored, so their round trips overlap.
+// sobj[slot] = sigmoid(objectness) of the warp tile's boxes; wbase = plane 0 of the (image, anchor) at the tile's first box;
+// E.flg = box slots of this batch.
+__device__ __forceinline__ int nth_slot(const unsigned (&w)[4], const int (&c)[4], int i)
+{
+    int j = 0;
+#pragma unroll
+    for (int q = 1; q < 4; ++q) j = (i >= c[q]) ? q : j;
+    const unsigned wsel = (j == 0) ? w[0] : ((j == 1) ? w[1] : ((j == 2) ? w[2] : w[3]));
+    const int cs = (j == 0) ? c[0] : ((j == 1) ? c[1] : ((j == 2) ? c[2] : c[3]));
+    return 32 * j + (int)__fns(wsel, 0, i - cs + 1);
+}
+
 template <int VEC>
 __device__ __forceinline__ void emit_batch(const RawParams &P, const RawLayer &Ly, EmitWarp &E, const float *sobj,
                                            const float *wbase, int b, int a, int wp0, int total)
@@ -102,7 +122,22 @@ __device__ __forceinline__ void emit_batch(const RawParams &P, const RawLayer &L
     const float thr = P.thr;
     const float *wcp = wbase + 5 * (size_t)F2;
     const int row_base = Ly.row_off + a * F2;                        // + p = row inside the image
-    __syncwarp();                                                    // queue entries and any/nan masks are visible
+    __syncwarp();                                                    // queue entries and flg/any/nan masks are visible
+    unsigned fw[4];
+    int fc[4], nflag = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        fw[j] = (j < VEC) ? E.flg[j] : 0u;
+        fc[j] = nflag;
+        nflag += __popc(fw[j]);
+    }
+    int sbs = -1;
+    float tx = 0.f, ty = 0.f, tw = 0.f, th = 0.f;
+    if (lane < nflag) {
+        sbs = nth_slot(fw, fc, lane);
+        const float *bp = wbase + sbs;
+        tx = bp[0]; ty = bp[(size_t)F2]; tw = bp[2 * (size_t)F2]; th = bp[3 * (size_t)F2];
+    }
     for (int e0 = 0; e0 < total; e0 += 128) {
         float t[4];
         unsigned en[4];
@@ -129,50 +164,105 @@ __device__ __forceinline__ void emit_batch(const RawParams &P, const RawLayer &L
         }
     }
     __syncwarp();
-    {
-        unsigned lw[4];
-        int lc[4], nlive = 0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            lw[j] = (j < VEC) ? (E.any[j] & ~E.nan[j]) : 0u;
-            lc[j] = nlive;
-            nlive += __popc(lw[j]);
-        }
-        for (int i = lane; i < nlive; i += 32) {
-            int j = 0;
-#pragma unroll
-            for (int q = 1; q < 4; ++q) j = (i >= lc[q]) ? q : j;
-            const unsigned wsel = (j == 0) ? lw[0] : ((j == 1) ? lw[1] : ((j == 2) ? lw[2] : lw[3]));
-            const int lcs = (j == 0) ? lc[0] : ((j == 1) ? lc[1] : ((j == 2) ? lc[2] : lc[3]));
-            const int bs = 32 * j + (int)__fns(wsel, 0, i - lcs + 1);
+    if (sbs >= 0 && (((E.any[sbs >> 5] & ~E.nan[sbs >> 5]) >> (sbs & 31)) & 1u))
+        E.box[sbs] = decode_box_v(tx, ty, tw, th, Ly.Fw, wp0 + sbs, Ly.aw[a], Ly.ah[a], Ly.stride);
+    for (int i = lane + 32; i < nflag; i += 32) {                    // more than 32 flagged boxes in the batch (dense inputs)
+        const int bs = nth_slot(fw, fc, i);
+        if (((E.any[bs >> 5] & ~E.nan[bs >> 5]) >> (bs & 31)) & 1u)
             E.box[bs] = decode_box(wbase + bs, F2, Ly.Fw, wp0 + bs, Ly.aw[a], Ly.ah[a], Ly.stride);
-        }
     }
     __syncwarp();
-    for (int q = lane; q < total; q += 32) {
-        const unsigned en = E.ent[q];
-        const int bs = (en >> 8) & 0x7F;
-        if ((en & 0x8000u) && !((E.nan[bs >> 5] >> (bs & 31)) & 1u)) {
-            const int k = en & 0x7F;
-            const float cls = __uint_as_float(E.cls[q]);
-            const float s = __fadd_rn(__fmul_rn(sobj[bs], cls), 0.0f);      // +0 canonicalises -0
-            const unsigned seg = (unsigned)(b * C + k);
-            const unsigned slot = atomicAdd(&P.seg_count[seg], 1u);
-            if (slot < (unsigned)P.cap_seg) {
-                uint4 *r = P.cand + ((size_t)seg * P.cap_seg + slot) * 2;
+    for (int q0 = 0; q0 < total; q0 += 128) {
+        unsigned slot[4], en[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int q = q0 + 32 * u + lane;
+            en[u] = 0u;
+            slot[u] = 0xFFFFFFFFu;
+            if (q < total) {
+                en[u] = E.ent[q];
+                const int bs = (en[u] >> 8) & 0x7F;
+                if ((en[u] & 0x8000u) && !((E.nan[bs >> 5] >> (bs & 31)) & 1u))
+                    slot[u] = atomicAdd(&P.seg_count[(unsigned)(b * C + (int)(en[u] & 0x7F))], 1u);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (slot[u] < (unsigned)P.cap_seg) {
+                const int q = q0 + 32 * u + lane;
+                const int bs = (en[u] >> 8) & 0x7F;
+                const float cls = __uint_as_float(E.cls[q]);
+                const float so = sobj[bs];
+                const float s = __fadd_rn(__fmul_rn(so, cls), 0.0f);       // +0 canonicalises -0
+                const unsigned seg = (unsigned)(b * C + (int)(en[u] & 0x7F));
+                uint4 *r = P.cand + ((size_t)seg * P.cap_seg + slot[u]) * 2;
                 const float4 bx = E.box[bs];
-                r[0] = make_uint4(__float_as_uint(s), (unsigned)(row_base + wp0 + bs), __float_as_uint(cls), __float_as_uint(sobj[bs]));
+                r[0] = make_uint4(__float_as_uint(s), (unsigned)(row_base + wp0 + bs), __float_as_uint(cls), __float_as_uint(so));
                 r[1] = make_uint4(__float_as_uint(bx.x), __float_as_uint(bx.y), __float_as_uint(bx.z), __float_as_uint(bx.w));
             }
         }
     }
     __syncwarp();
-    if (lane < 4) { E.any[lane] = 0u; E.nan[lane] = 0u; }
+    if (lane < 4) { E.any[lane] = 0u; E.nan[lane] = 0u; E.flg[lane] = 0u; }
 }
 
-// Phase 2 of a warp tile (32*VEC consecutive boxes, lane L owns boxes L*VEC .. L*VEC+VEC-1, bits[v][w] = flagged classes):
-// the flag words are expanded into a queue of (box slot, class) pairs by the whole warp, box by box, and the
-// queue is resolved in batches of whole boxes.  sobj must already hold sigmoid(objectness) per box slot.
+// Per-lane flagged-pair count and the warp's exclusive prefix (queue order: lane-major, then box, then class ascending).
+template <int VEC, int NW>
+__device__ __forceinline__ int pair_prefix(const float (&lth)[VEC], const unsigned (&bits)[VEC][NW], unsigned (&anyv)[VEC],
+                                           int &first)
+{
+    const int lane = threadIdx.x & 31;
+    int cntl = 0;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+        unsigned any = 0u;
+        int c = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) { any |= bits[v][w]; c += __popc(bits[v][w]); }
+        if (lth[v] == kInf) { any = 0u; c = 0; }
+        anyv[v] = any;
+        cntl += c;
+    }
+    int incl = cntl;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    first = incl - cntl;
+    return __shfl_sync(0xFFFFFFFFu, incl, 31);
+}
+
+// Every lane writes its own pairs into the queue at the position the prefix sum gives it; flg gets the flagged box slots.
+template <int VEC, int NW>
+__device__ __forceinline__ void queue_pairs(const unsigned (&bits)[VEC][NW], const unsigned (&anyv)[VEC], int first,
+                                            unsigned short *ent, unsigned *flg)
+{
+    const int lane = threadIdx.x & 31;
+    int q = first;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v)
+        if (anyv[v]) {
+            const int bs = lane * VEC + v;
+            atomicOr(&flg[bs >> 5], 1u << (bs & 31));
+            const unsigned hdr = (unsigned)bs << 8;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                unsigned m = bits[v][w];
+                while (m) {
+                    const int k = __ffs(m) - 1;
+                    m &= m - 1u;
+                    ent[q++] = (unsigned short)(hdr | (unsigned)(32 * w + k));
+                }
+            }
+        }
+}
+
+// Phase 2 of a warp tile (32*VEC consecutive boxes, lane L owns boxes L*VEC .. L*VEC+VEC-1, bits[v][w] = flagged classes).
+// Common case (at most K1_QCAP flagged pairs in the tile): every lane writes its own pairs into the queue at the
+// position a warp prefix sum gives it, and the queue is resolved as one batch.  Dense tiles fall back to expanding the
+// flag words box by box and resolving the queue in batches of whole boxes.  sobj must already hold
+// sigmoid(objectness) per box slot.
 template <int VEC, int NW>
 __device__ __forceinline__ void emit_pairs(const RawParams &P, const RawLayer &Ly, int ba, int wp0,
                                            const float (&lth)[VEC], unsigned (&bits)[VEC][NW], EmitWarp &E, const float *sobj)
@@ -180,20 +270,21 @@ __device__ __forceinline__ void emit_pairs(const RawParams &P, const RawLayer &L
     const unsigned FULL = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
     const int b = ba / 3, a = ba - 3 * b;
+    unsigned anyv[VEC];
+    int first;
+    const int total = pair_prefix<VEC, NW>(lth, bits, anyv, first);
+    if (total == 0) return;                                          // warp-uniform
     const float *wbase = Ly.raw + ((size_t)ba * (5 + P.C)) * Ly.F2 + wp0;
-    unsigned flagged[VEC];
-    unsigned any_lane = 0u;
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) {
-        unsigned any = 0u;
-#pragma unroll
-        for (int w = 0; w < NW; ++w) any |= bits[v][w];
-        if (lth[v] == kInf) any = 0u;
-        flagged[v] = __ballot_sync(FULL, any != 0u);
-        any_lane |= flagged[v];
+    if (lane < 4) { E.any[lane] = 0u; E.nan[lane] = 0u; E.flg[lane] = 0u; }
+    __syncwarp();
+    if (total <= K1_QCAP) {
+        queue_pairs<VEC, NW>(bits, anyv, first, E.ent, E.flg);
+        emit_batch<VEC>(P, Ly, E, sobj, wbase, b, a, wp0, total);
+        return;
     }
-    if (any_lane == 0u) return;                                      // warp-uniform
-    if (lane < 4) { E.any[lane] = 0u; E.nan[lane] = 0u; }
+    unsigned flagged[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) flagged[v] = __ballot_sync(FULL, anyv[v] != 0u);
     int qb = 0;
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
@@ -205,8 +296,10 @@ __device__ __forceinline__ void emit_pairs(const RawParams &P, const RawLayer &L
             int n = 0;
 #pragma unroll
             for (int w = 0; w < NW; ++w) { m[w] = __shfl_sync(FULL, bits[v][w], L); n += __popc(m[w]); }
-            if (qb + n > K1_QCAP) { emit_batch<VEC>(P, Ly, E, sobj, wbase, b, a, wp0, qb); qb = 0; }
-            const unsigned hdr = (unsigned)(L * VEC + v) << 8;
+            if (qb + n > K1_QCAP) { emit_batch<VEC>(P, Ly, E, sobj, wbase, b, a, wp0, qb); qb = 0; __syncwarp(); }
+            const int bs = L * VEC + v;
+            if (lane == 0) E.flg[bs >> 5] |= 1u << (bs & 31);
+            const unsigned hdr = (unsigned)bs << 8;
 #pragma unroll
             for (int w = 0; w < NW; ++w) {
                 if ((m[w] >> lane) & 1u) E.ent[qb + __popc(m[w] & ((1u << lane) - 1u))] = (unsigned short)(hdr | (32 * w + lane));
@@ -386,23 +479,25 @@ __device__ __forceinline__ void emit_tile(const RawParams &P, const RawLayer &Ly
 #pragma unroll
         for (int w = 0; w < NW; ++w) bits[0][w] = inb ? P.flags[(size_t)w * P.BM4 + r] : 0u;
     }
+    // sigmoid(objectness) is requested together with the flag words (one round trip, not two)
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (inb) {
+        if (VEC == 4) o = *reinterpret_cast<const float4 *>(P.objtab + r);
+        else o.x = P.objtab[r];
+    }
     unsigned any = 0u;
 #pragma unroll
     for (int v = 0; v < VEC; ++v)
 #pragma unroll
         for (int w = 0; w < NW; ++w) any |= bits[v][w];
     if (!__any_sync(0xFFFFFFFFu, any != 0u)) return;                 // warp-uniform: nothing flagged in these 32*VEC boxes
-    if (VEC == 4) {
-        const float4 o = inb ? *reinterpret_cast<const float4 *>(P.objtab + r) : make_float4(0.f, 0.f, 0.f, 0.f);
-        *reinterpret_cast<float4 *>(&sm.sobj[warp][lane * 4]) = o;
-    } else {
-        sm.sobj[warp][lane] = inb ? P.objtab[r] : 0.0f;
-    }
+    if (VEC == 4) *reinterpret_cast<float4 *>(&sm.sobj[warp][lane * 4]) = o;
+    else sm.sobj[warp][lane] = o.x;
     emit_pairs<VEC, NW>(P, Ly, ba, (tile * K1_THREADS + warp * 32) * VEC, lth, bits, sm.e[warp], sm.sobj[warp]);
 }
 
 #ifndef YL_EMIT_MINB
-#define YL_EMIT_MINB 10
+#define YL_EMIT_MINB 8
 #endif
 template <int NW>
 __global__ void __launch_bounds__(K1_THREADS, YL_EMIT_MINB)

@@ -107,7 +107,10 @@ constexpr int SMALL_W = SMALL_R / 32;
 constexpr int SMALL_THREADS = 128;
 constexpr int SMALL_WARPS = SMALL_THREADS / 32;
 constexpr int SMALL_EPT = SMALL_R / SMALL_THREADS;      // records per thread, at most
-constexpr int NBIN = 64;
+#ifndef YL_NMS_NBIN
+#define YL_NMS_NBIN 64
+#endif
+constexpr int NBIN = YL_NMS_NBIN;                     // bins per table (at most 64: bin numbers are packed in 6 bits)
 #ifndef YL_NMS_QCAP
 #define YL_NMS_QCAP 512
 #endif
@@ -321,19 +324,17 @@ k_segment_nms_bins(uint4 *__restrict__ cand, const unsigned *__restrict__ seg_co
         }
     }
     __syncthreads();
-    // prefix / suffix OR over the bins: 6 tables x nwp word pairs, one lane per chain
+    // prefix / suffix OR over the bins: 6 tables x nwp word pairs, one lane per chain (direction by index arithmetic,
+    // so the lanes of both directions run the same instruction stream)
     if (tid < 6 * (SMALL_W / 2)) {
         const int t = tid >> 2, wp = tid & 3;
         if (wp < nwp) {
             unsigned long long *p = &S.b.tab[t][wp][0];
+            const int step = (t & 1) ? 1 : -1;
+            int pos = (t & 1) ? 0 : NBIN - 1;
             unsigned long long acc = 0ull;
-            if (t & 1) {
 #pragma unroll 8
-                for (int bnn = 0; bnn < NBIN; ++bnn) { acc |= p[bnn]; p[bnn] = acc; }
-            } else {
-#pragma unroll 8
-                for (int bnn = NBIN - 1; bnn >= 0; --bnn) { acc |= p[bnn]; p[bnn] = acc; }
-            }
+            for (int i = 0; i < NBIN; ++i, pos += step) { acc |= p[pos]; p[pos] = acc; }
         }
     }
     __syncthreads();
@@ -359,22 +360,20 @@ k_segment_nms_bins(uint4 *__restrict__ cand, const unsigned *__restrict__ seg_co
                     const int rel = j - 64 * wp;                 // rows of this warp lie in one 64-block: rel >= 0
                     const unsigned long long lim = (rel >= 64) ? ~0ull : ((1ull << rel) - 1ull);
                     const unsigned long long cw = act ? (~ex & lim) : 0ull;
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        unsigned c = h ? (unsigned)(cw >> 32) : (unsigned)cw;
-                        const int ibase = 64 * wp + 32 * h;
-                        while (__any_sync(FULL, c != 0u)) {
-                            const bool has = c != 0u;
-                            const unsigned m = __ballot_sync(FULL, has);
-                            if (has) {
-                                const int ii = __ffs(c) - 1;
-                                c &= c - 1u;
-                                const unsigned slot = qcount + __popc(m & lt);
-                                if (slot < (unsigned)QCAP_W) myq[slot] = (unsigned short)((j << 8) | (ibase + ii));
-                                else overflow = true;
-                            }
-                            qcount += __popc(m);
+                    unsigned c0 = (unsigned)cw, c1 = (unsigned)(cw >> 32);
+                    const int ibase = 64 * wp;
+                    while (__any_sync(FULL, (c0 | c1) != 0u)) {  // one pair per lane and round, low word first
+                        const bool has = (c0 | c1) != 0u;
+                        const unsigned m = __ballot_sync(FULL, has);
+                        if (has) {
+                            int ii;
+                            if (c0) { ii = __ffs(c0) - 1; c0 &= c0 - 1u; }
+                            else { ii = 32 + __ffs(c1) - 1; c1 &= c1 - 1u; }
+                            const unsigned slot = qcount + __popc(m & lt);
+                            if (slot < (unsigned)QCAP_W) myq[slot] = (unsigned short)((j << 8) | (ibase + ii));
+                            else overflow = true;
                         }
+                        qcount += __popc(m);
                     }
                 }
             }

@@ -188,7 +188,8 @@ class HeadPostprocessor:
     """
 
     def __init__(self, batch, grid_sizes, num_classes, conf_thre, nms_thre, device=None, cap_seg=_DEFAULT_CAP_SEG,
-                 cap_out=_DEFAULT_CAP_OUT, n_groups=1, anchors=ANCHORS_PX, anchor_mask=ANCHOR_MASK):
+                 cap_out=_DEFAULT_CAP_OUT, n_groups=1, anchors=ANCHORS_PX, anchor_mask=ANCHOR_MASK, side_priority=0,
+                 mode="nms_side"):
         self.L = _cabi.lib()
         self.device = torch.device(device if device is not None else "cuda")
         self.B, self.Fs, self.C = int(batch), [int(f) for f in grid_sizes], int(num_classes)
@@ -203,9 +204,10 @@ class HeadPostprocessor:
             self.ws = _Workspace(self.device, self.B, self.M, self.C, self.cap_seg)
             self.rows = torch.empty((self.B, self.cap_out, 7), dtype=torch.float32, device=self.device)
             self.meta = torch.zeros((3 * self.B,), dtype=torch.int32, device=self.device)
-            self.side = torch.cuda.Stream(device=self.device)
+            self.side = torch.cuda.Stream(device=self.device, priority=side_priority)
+        self.mode = mode
         self.graph = None
-        # kernels launched per run(): per group flag + emit + segment NMS (warp tier) + big tier + gather (+ 1 memset node)
+        # kernels launched per run(): per group flag + emit + segment NMS + fix-up (+ 1 memset node)
         self.launches_per_run = self.n_groups * 5
 
     def run(self, head_outputs):
@@ -216,9 +218,17 @@ class HeadPostprocessor:
         G = self.n_groups
         for g in range(G):
             i0, i1 = B * g // G, B * (g + 1) // G
-            _cabi.check(L.yl_filter_raw(rp, self.fs, len(self.Fs), B, C, self.anch, self.mask, self.conf, self.ws.ptr(),
-                                        self.ws.nbytes, M, self.cap_seg, i0, i1 - i0, main.cuda_stream))
-            self.side.wait_stream(main)
+            if self.mode == "emit_side":
+                # streaming flag kernels back to back on the main stream; everything else follows on the side stream
+                _cabi.check(L.yl_filter_raw_stage(rp, self.fs, len(self.Fs), B, C, self.anch, self.mask, self.conf, self.ws.ptr(),
+                                                  self.ws.nbytes, M, self.cap_seg, i0, i1 - i0, 1, main.cuda_stream))
+                self.side.wait_stream(main)
+                _cabi.check(L.yl_filter_raw_stage(rp, self.fs, len(self.Fs), B, C, self.anch, self.mask, self.conf, self.ws.ptr(),
+                                                  self.ws.nbytes, M, self.cap_seg, i0, i1 - i0, 2, self.side.cuda_stream))
+            else:
+                _cabi.check(L.yl_filter_raw(rp, self.fs, len(self.Fs), B, C, self.anch, self.mask, self.conf, self.ws.ptr(),
+                                            self.ws.nbytes, M, self.cap_seg, i0, i1 - i0, main.cuda_stream))
+                self.side.wait_stream(main)
             _cabi.check(L.yl_nms(self.ws.ptr(), self.ws.nbytes, B, M, C, self.cap_seg, self.nms, self.rows.data_ptr(),
                                  self.cap_out, self.meta.data_ptr(), i0, i1 - i0, self.side.cuda_stream))
         main.wait_stream(self.side)
