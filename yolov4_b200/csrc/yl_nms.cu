@@ -85,7 +85,7 @@ __device__ __forceinline__ void store_row(float *o, const float4 &box, unsigned 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Small tier (the common case: ~150 candidates per (image,class) at conf 1e-4).  Everything in ~24 KB of shared memory.
+// Small tier (the common case: ~150 candidates per (image,class) at conf 1e-4).  Everything in ~21 KB of shared memory.
 //   1. rank sort on the 32-bit score key (LDS.128 per four keys, one compare + predicated add per key); if two records
 //      tie on the score the ranks collide, which is detected, and the segment is ranked again on the unique 64-bit key
 //      (score, row);
@@ -108,7 +108,7 @@ constexpr int SMALL_THREADS = 128;
 constexpr int SMALL_WARPS = SMALL_THREADS / 32;
 constexpr int SMALL_EPT = SMALL_R / SMALL_THREADS;      // records per thread, at most
 #ifndef YL_NMS_NBIN
-#define YL_NMS_NBIN 64
+#define YL_NMS_NBIN 48
 #endif
 constexpr int NBIN = YL_NMS_NBIN;                     // bins per table (at most 64: bin numbers are packed in 6 bits)
 #ifndef YL_NMS_QCAP
@@ -116,7 +116,7 @@ constexpr int NBIN = YL_NMS_NBIN;                     // bins per table (at most
 #endif
 constexpr int QCAP_W = YL_NMS_QCAP;                     // queued pairs per warp
 #ifndef YL_NMS_MINB
-#define YL_NMS_MINB 9
+#define YL_NMS_MINB 10
 #endif
 constexpr int AREA_BIN_OFF = (127 + 4) << 2;            // float bits >> 21 of 16.0f: areas below 16 px^2 share bin 0
 
