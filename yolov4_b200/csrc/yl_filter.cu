@@ -758,70 +758,166 @@ k_filter_raw(const __grid_constant__ RawParams P)
     else filter_tile<1, NW>(P, P.layer[l], tile, ba, sm);
 }
 
-// One warp per decoded row (5+C contiguous floats, <= 133): coalesced 128-byte reads, ballot-free emission.
+// Dense front end: rows of 5+C contiguous floats.  Four consecutive rows are exactly (5+C) float4s, and a group of
+// four rows that starts at a row index divisible by four is 16-byte aligned, so a warp streams two such groups per
+// round with 128-bit loads (all of them in flight before the first use), parks them in shared memory and then walks the
+// eight rows: NaN-propagating row pre-filter, per-class test, one record per surviving pair.
 constexpr int KD_THREADS = 256;
+constexpr int KD_WARPS = KD_THREADS / 32;
 constexpr int KD_MAXJ = (5 + YL_MAX_CLASSES + 31) / 32;
+constexpr int KD_GROUPS = 2;                                // 4-row groups per warp and round
 
+// One decoded row held one element per lane and slot: e[j] = row[32 j + lane].
+template <int NJ>
+__device__ __forceinline__ void dense_row(const float (&e)[NJ], int nch, int C, int num_classes, float thr,
+                                          int cap_seg, long r, long M, uint4 *__restrict__ cand, unsigned *__restrict__ seg_count)
+{
+    const int lane = threadIdx.x & 31;
+    const float obj = __shfl_sync(0xFFFFFFFFu, e[0], 4);
+    bool pass[NJ];
+    bool any = false, anyn = false, has_nan = false;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        const int idx = 32 * j + lane;
+        pass[j] = (idx >= 5 && idx < nch) && (__fmul_rn(e[j], obj) >= thr);    // utils.py:170
+        any |= pass[j];
+        anyn |= pass[j] && idx < 5 + num_classes;
+        has_nan |= (idx >= 5 && idx < 5 + num_classes) && (e[j] != e[j]);
+    }
+    if (obj >= 0.0f) {
+        // Row pre-filter obj * max_{c < num_classes} cls >= thr (utils.py:139-148).  For obj >= 0, fl(obj*x) is monotone in x,
+        // so without NaNs the row passes exactly when one of its first num_classes classes passes the per-class test:
+        // no max reduction for the ~99 % of rows that produce nothing.
+        if (!__any_sync(0xFFFFFFFFu, anyn)) return;
+        if (__any_sync(0xFFFFFFFFu, has_nan)) return;                 // torch.max propagates NaN: NaN >= thr is False
+    } else {
+        // negative / NaN objectness (not a sigmoid output): literal form, max with torch.max NaN propagation
+        float mx = -kInf;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const int idx = 32 * j + lane;
+            if (idx >= 5 && idx < 5 + num_classes) mx = fmaxf(mx, e[j]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+        if (__any_sync(0xFFFFFFFFu, has_nan) || !(__fmul_rn(obj, mx) >= thr)) return;
+        if (!__any_sync(0xFFFFFFFFu, any)) return;
+    }
+    // image / row of the few rows that get here (the 64-bit division costs more than the rest of the row test)
+    int b;
+    unsigned row;
+    if (r < 0x7FFFFFFFL && M < 0x7FFFFFFFL) { b = (int)((unsigned)r / (unsigned)M); row = (unsigned)r - (unsigned)b * (unsigned)M; }
+    else { b = (int)(r / M); row = (unsigned)(r - (long)b * M); }
+    const float cx = __shfl_sync(0xFFFFFFFFu, e[0], 0), cy = __shfl_sync(0xFFFFFFFFu, e[0], 1);
+    const float w = __shfl_sync(0xFFFFFFFFu, e[0], 2), h = __shfl_sync(0xFFFFFFFFu, e[0], 3);
+    const float hw = __fmul_rn(w, 0.5f), hh = __fmul_rn(h, 0.5f);          // utils.py:117-126
+    const uint4 corners = make_uint4(__float_as_uint(__fsub_rn(cx, hw)), __float_as_uint(__fsub_rn(cy, hh)),
+                                     __float_as_uint(__fadd_rn(cx, hw)), __float_as_uint(__fadd_rn(cy, hh)));
+#pragma unroll
+    for (int j = 0; j < NJ; ++j)
+        if (pass[j]) {
+            const int k = 32 * j + lane - 5;
+            const float s = __fadd_rn(__fmul_rn(obj, e[j]), 0.0f);        // nms score = obj*cls (utils.py:209)
+            const unsigned seg = (unsigned)(b * C + k);
+            const unsigned slot = atomicAdd(&seg_count[seg], 1u);
+            if (slot < (unsigned)cap_seg) {
+                uint4 *r = cand + ((size_t)seg * cap_seg + slot) * 2;
+                r[0] = make_uint4(__float_as_uint(s), row, __float_as_uint(e[j]), __float_as_uint(obj));
+                r[1] = corners;
+            }
+        }
+}
+
+template <int NJ>
 __global__ void __launch_bounds__(KD_THREADS)
-k_filter_dense(const float *__restrict__ pred, long M, long M4, int C, int num_classes, float thr, int cap_seg,
-               int img_first, long n_rows,
+k_filter_dense(const float *__restrict__ pred, long M, int C, int num_classes, float thr, int cap_seg,
+               long row_first, long row_end, long rows_total,
                uint4 *__restrict__ cand, unsigned *__restrict__ seg_count)
+{
+    __shared__ __align__(16) float stage[KD_WARPS][KD_GROUPS][4 * 32 * NJ];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long wid = ((long)blockIdx.x * KD_THREADS + threadIdx.x) >> 5;
+    const long nwarps = ((long)gridDim.x * KD_THREADS) >> 5;
+    const int nch = 5 + C;
+    const long g_first = row_first >> 2, g_end = (row_end + 3) >> 2;          // 4-row groups that touch [row_first, row_end)
+    const long total4 = rows_total * nch / 4;                                 // whole float4s of the tensor (rows_total*nch*4 bytes)
+    const float4 *p4 = reinterpret_cast<const float4 *>(pred);
+    float4 v[KD_GROUPS][NJ];
+    auto load_round = [&](long g0) {
+#pragma unroll
+        for (int q = 0; q < KD_GROUPS; ++q) {
+            const long base4 = (g0 + q) * nch;                                // group g = float4s [g*nch, (g+1)*nch)
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                const int i = 32 * j + lane;
+                v[q][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (i < nch && g0 + q < g_end) {
+                    if (base4 + i < total4) {
+                        const float4 *src = p4 + base4 + i;
+                        asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                                     : "=f"(v[q][j].x), "=f"(v[q][j].y), "=f"(v[q][j].z), "=f"(v[q][j].w) : "l"(src));
+                    } else if (base4 + i == total4) {
+                        // the tensor ends inside this float4 (rows_total * (5+C) not a multiple of 4): scalar loads
+                        const long rem = rows_total * nch - 4 * total4;
+                        const float *src = pred + 4 * total4;
+                        if (rem > 0) v[q][j].x = src[0];
+                        if (rem > 1) v[q][j].y = src[1];
+                        if (rem > 2) v[q][j].z = src[2];
+                    }
+                }
+            }
+        }
+    };
+    long g0 = g_first + wid * KD_GROUPS;
+    if (g0 < g_end) load_round(g0);
+    while (g0 < g_end) {
+#pragma unroll
+        for (int q = 0; q < KD_GROUPS; ++q)
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                const int i = 32 * j + lane;
+                if (i < nch) reinterpret_cast<float4 *>(stage[warp][q])[i] = v[q][j];
+            }
+        __syncwarp();
+        const long gn = g0 + nwarps * KD_GROUPS;
+        if (gn < g_end) load_round(gn);                                       // the next round is in flight while this one is walked
+        const long r0 = g0 * 4;
+        const int rr_lo = (int)max(0L, row_first - r0), rr_hi = (int)min((long)(4 * KD_GROUPS), row_end - r0);
+#pragma unroll 1
+        for (int rr = rr_lo; rr < rr_hi; ++rr) {                              // rows of this round inside [row_first, row_end)
+            const float *st = stage[warp][rr >> 2] + (rr & 3) * nch;
+            float e[NJ];
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                const int idx = 32 * j + lane;
+                e[j] = (idx < nch) ? st[idx] : 0.0f;
+            }
+            dense_row<NJ>(e, nch, C, num_classes, thr, cap_seg, r0 + rr, M, cand, seg_count);
+        }
+        __syncwarp();                                                         // all lanes have read the stage
+        g0 = gn;
+    }
+}
+
+// Fallback for a tensor whose base is not 16-byte aligned: one warp per row, scalar loads.
+__global__ void __launch_bounds__(KD_THREADS)
+k_filter_dense_unaligned(const float *__restrict__ pred, long M, int C, int num_classes, float thr, int cap_seg,
+                         long row_first, long row_end, uint4 *__restrict__ cand, unsigned *__restrict__ seg_count)
 {
     const int lane = threadIdx.x & 31;
     const long wid = ((long)blockIdx.x * KD_THREADS + threadIdx.x) >> 5;
     const long nwarps = ((long)gridDim.x * KD_THREADS) >> 5;
     const int nch = 5 + C;
     const int nj = (nch + 31) >> 5;
-    for (long r = wid; r < n_rows; r += nwarps) {
-        const int b = img_first + (int)(r / M);
-        const unsigned row = (unsigned)(r % M);
-        const float *p = pred + ((size_t)b * M + row) * nch;
+    for (long r = row_first + wid; r < row_end; r += nwarps) {
+        const float *p = pred + (size_t)r * nch;
         float e[KD_MAXJ];
 #pragma unroll
         for (int j = 0; j < KD_MAXJ; ++j) {
             const int idx = 32 * j + lane;
             e[j] = (j < nj && idx < nch) ? ldg_stream1(p + idx) : 0.0f;
         }
-        const float obj = __shfl_sync(0xFFFFFFFFu, e[0], 4);
-        // row pre-filter obj * max_c cls >= thr with torch.max NaN propagation (utils.py:139-148)
-        float mx = -kInf;
-        bool has_nan = false;
-#pragma unroll
-        for (int j = 0; j < KD_MAXJ; ++j) {
-            const int idx = 32 * j + lane;
-            if (j < nj && idx >= 5 && idx < 5 + num_classes) { has_nan |= (e[j] != e[j]); mx = fmaxf(mx, e[j]); }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
-        has_nan = __any_sync(0xFFFFFFFFu, has_nan);
-        if (has_nan || !(__fmul_rn(obj, mx) >= thr)) continue;
-        bool pass[KD_MAXJ];
-        bool any = false;
-#pragma unroll
-        for (int j = 0; j < KD_MAXJ; ++j) {
-            const int idx = 32 * j + lane;
-            pass[j] = (j < nj && idx >= 5 && idx < nch) && (__fmul_rn(e[j], obj) >= thr);    // utils.py:170
-            any |= pass[j];
-        }
-        if (!__any_sync(0xFFFFFFFFu, any)) continue;
-        const float cx = __shfl_sync(0xFFFFFFFFu, e[0], 0), cy = __shfl_sync(0xFFFFFFFFu, e[0], 1);
-        const float w = __shfl_sync(0xFFFFFFFFu, e[0], 2), h = __shfl_sync(0xFFFFFFFFu, e[0], 3);
-        const float hw = __fmul_rn(w, 0.5f), hh = __fmul_rn(h, 0.5f);          // utils.py:117-126
-        const uint4 corners = make_uint4(__float_as_uint(__fsub_rn(cx, hw)), __float_as_uint(__fsub_rn(cy, hh)),
-                                         __float_as_uint(__fadd_rn(cx, hw)), __float_as_uint(__fadd_rn(cy, hh)));
-#pragma unroll
-        for (int j = 0; j < KD_MAXJ; ++j)
-            if (pass[j]) {
-                const int k = 32 * j + lane - 5;
-                const float s = __fadd_rn(__fmul_rn(obj, e[j]), 0.0f);        // nms score = obj*cls (utils.py:209)
-                const unsigned seg = (unsigned)(b * C + k);
-                const unsigned slot = atomicAdd(&seg_count[seg], 1u);
-                if (slot < (unsigned)cap_seg) {
-                    uint4 *r = cand + ((size_t)seg * cap_seg + slot) * 2;
-                    r[0] = make_uint4(__float_as_uint(s), row, __float_as_uint(e[j]), __float_as_uint(obj));
-                    r[1] = corners;
-                }
-            }
+        dense_row<KD_MAXJ>(e, nch, C, num_classes, thr, cap_seg, r, M, cand, seg_count);
     }
 }
 
@@ -1036,12 +1132,32 @@ extern "C" int yl_filter_dense(const float *pred, int B, long M, int C, int num_
     if (ws_bytes < L.total) return YL_ERR_WORKSPACE;
     if (img_count == 0) return YL_OK;
     char *w = (char *)ws;
-    const long n_rows = (long)img_count * M;
-    const long blocks_needed = (n_rows * 32 + KD_THREADS - 1) / KD_THREADS;
-    const int grid = (int)(blocks_needed < 148L * 64 ? blocks_needed : 148L * 64);
-    k_filter_dense<<<grid, KD_THREADS, 0, (cudaStream_t)stream>>>(
-        pred, M, L.M4, C, num_classes, conf_thre, cap_seg, img_first, n_rows, (uint4 *)(w + L.off_cand),
-        (unsigned *)(w + L.off_seg_count));
+    const long row_first = (long)img_first * M, row_end = (long)(img_first + img_count) * M, rows_total = (long)B * M;
+    uint4 *cand = (uint4 *)(w + L.off_cand);
+    unsigned *seg_count = (unsigned *)(w + L.off_seg_count);
+    if (((uintptr_t)pred) % 16 == 0) {
+        const long warps_needed = ((row_end - row_first) / 4 + KD_GROUPS) / KD_GROUPS;
+        const long blocks_needed = (warps_needed + KD_WARPS - 1) / KD_WARPS;
+        const int grid = (int)(blocks_needed < 148L * 8 ? blocks_needed : 148L * 8);
+        switch ((5 + C + 31) / 32) {
+#define YL_KD_CASE(NJ_)                                                                                               \
+    case NJ_:                                                                                                         \
+        k_filter_dense<NJ_><<<grid, KD_THREADS, 0, (cudaStream_t)stream>>>(pred, M, C, num_classes, conf_thre, cap_seg, \
+                                                                          row_first, row_end, rows_total, cand, seg_count); \
+        break;
+            YL_KD_CASE(1) YL_KD_CASE(2) YL_KD_CASE(3) YL_KD_CASE(4)
+        default:
+            k_filter_dense<KD_MAXJ><<<grid, KD_THREADS, 0, (cudaStream_t)stream>>>(pred, M, C, num_classes, conf_thre, cap_seg,
+                                                                                  row_first, row_end, rows_total, cand, seg_count);
+            break;
+#undef YL_KD_CASE
+        }
+    } else {
+        const long blocks_needed = ((row_end - row_first) * 32 + KD_THREADS - 1) / KD_THREADS;
+        const int grid = (int)(blocks_needed < 148L * 64 ? blocks_needed : 148L * 64);
+        k_filter_dense_unaligned<<<grid, KD_THREADS, 0, (cudaStream_t)stream>>>(pred, M, C, num_classes, conf_thre, cap_seg, row_first,
+                                                                               row_end, cand, seg_count);
+    }
     YL_LAUNCH_CHECK();
     return YL_OK;
 }

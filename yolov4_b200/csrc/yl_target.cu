@@ -5,7 +5,9 @@
 //                      obj_mask / tgt_mask / tgt_scale / target at the matched cells (:304-369),
 //                      resolving same-cell collisions the way the reference's sequential loop does:
 //                      scalar fields last-writer-wins, class one-hots accumulate.
-// The dense zero background of target / tgt_mask / tgt_scale is written with cudaMemsetAsync.
+// The dense zero background of target / tgt_mask / tgt_scale (:156-167, 99.9 % of the 16 MB/image this path writes) is
+// stored by k_target_objmask itself, 128 bits at a time, before it computes its cells' IoUs: the pass runs at the pace
+// of the HBM writes and the IoU arithmetic hides underneath instead of following three memsets.
 #include "yl_common.cuh"
 #include "../../include/yolo_head.h"
 
@@ -43,28 +45,59 @@ __device__ __forceinline__ float iou_xywh(float ax, float ay, float aw, float ah
     return __fdiv_rn(ai, __fsub_rn(__fadd_rn(__fmul_rn(aw, ah), __fmul_rn(bw, bh)), ai));
 }
 
+// The CTA zeroes n floats at p (4-byte aligned): scalar head up to a 16-byte boundary, float4 body, scalar tail.
+__device__ __forceinline__ void cta_zero(float *p, int n)
+{
+    int head = (int)(((16u - (unsigned)((uintptr_t)p & 15u)) & 15u) >> 2);
+    if (head > n) head = n;
+    if ((int)threadIdx.x < head) p[threadIdx.x] = 0.0f;
+    float4 *p4 = reinterpret_cast<float4 *>(p + head);
+    const int n4 = (n - head) >> 2;
+#pragma unroll 4
+    for (int i = threadIdx.x; i < n4; i += TG_THREADS) p4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int tail = head + 4 * n4 + (int)threadIdx.x;
+    if (tail < n) p[tail] = 0.0f;
+}
+
 __device__ __forceinline__ bool bounded(float v) { return fabsf(v) <= 1e18f; }   // false for NaN / inf / huge
 
 __global__ void __launch_bounds__(TG_THREADS)
 k_target_objmask(const float *__restrict__ pred, long s0, long s1, long s2, long s3, long s4,
-                 const float *__restrict__ labels, int F, int K, float stride, float ignore_thre,
-                 float *__restrict__ obj_mask)
+                 const float *__restrict__ labels, int F, int K, int C, float stride, float ignore_thre,
+                 float *__restrict__ obj_mask, float *__restrict__ target, float *__restrict__ tgt_mask,
+                 float *__restrict__ tgt_scale)
 {
-    __shared__ float tb[TG_MAXK][4];
+    __shared__ __align__(16) float tb[TG_MAXK][4];
+    __shared__ __align__(16) float tc[TG_MAXK][4];       // GT corners (x1, y1, x2, y2) for the overlap pre-test
     __shared__ float tcls[TG_MAXK];
+    __shared__ float tarea[TG_MAXK];
     __shared__ unsigned char tsimple[TG_MAXK];
     __shared__ int sh_n;
     const int b = blockIdx.y;
-    const int n = load_truth(labels, b, K, stride, tb, tcls, &sh_n);
     const int cells = 3 * F * F;
+    {
+        // zero background of this CTA's cells (contiguous runs in all three tensors); k_target_scatter follows in stream order
+        const int c0 = blockIdx.x * TG_THREADS;
+        const int nc = min(TG_THREADS, cells - c0);
+        const size_t g0 = (size_t)b * cells + c0;
+        cta_zero(target + g0 * (5 + C), nc * (5 + C));
+        cta_zero(tgt_mask + g0 * (4 + C), nc * (4 + C));
+        cta_zero(tgt_scale + g0 * 2, nc * 2);
+    }
+    const int n = load_truth(labels, b, K, stride, tb, tcls, &sh_n);
     const int cell = blockIdx.x * TG_THREADS + threadIdx.x;
     if (n == 0) {                                                     // :225-227 obj_mask stays 1
         if (cell < cells) obj_mask[(size_t)b * cells + cell] = 1.0f;
         return;
     }
-    for (int t = threadIdx.x; t < n; t += TG_THREADS)
+    for (int t = threadIdx.x; t < n; t += TG_THREADS) {
         tsimple[t] = bounded(tb[t][0]) && bounded(tb[t][1]) && bounded(tb[t][2]) && bounded(tb[t][3]) &&
                      (__fmul_rn(tb[t][2], tb[t][3]) >= 0.0f);    // union = area_a + area_b stays > 0
+        const float bhw = __fmul_rn(tb[t][2], 0.5f), bhh = __fmul_rn(tb[t][3], 0.5f);
+        tc[t][0] = __fsub_rn(tb[t][0], bhw); tc[t][1] = __fsub_rn(tb[t][1], bhh);
+        tc[t][2] = __fadd_rn(tb[t][0], bhw); tc[t][3] = __fadd_rn(tb[t][1], bhh);
+        tarea[t] = __fmul_rn(tb[t][2], tb[t][3]);
+    }
     __syncthreads();
     if (cell >= cells) return;
     const int a = cell / (F * F);
@@ -74,25 +107,39 @@ k_target_objmask(const float *__restrict__ pred, long s0, long s1, long s2, long
     const float ax = pp[0], ay = pp[s4], aw = pp[2 * s4], ah = pp[3 * s4];
     // Fast path: with all coordinates finite and bounded and a strictly positive pred area, a GT that does not
     // overlap the cell's box has IoU exactly +0 (no NaN, no overflow), so only overlapping pairs need the division.
-    const bool csimple = bounded(ax) && bounded(ay) && bounded(aw) && bounded(ah) && (__fmul_rn(aw, ah) > 0.0f);
+    // (and a non-negative threshold: an IoU of exactly 0 must not count as "above")
+    const bool csimple = bounded(ax) && bounded(ay) && bounded(aw) && bounded(ah) && (__fmul_rn(aw, ah) > 0.0f) &&
+                         (ignore_thre >= 0.0f);
     const float ahw = __fmul_rn(aw, 0.5f), ahh = __fmul_rn(ah, 0.5f);
     const float ax1 = __fsub_rn(ax, ahw), ay1 = __fsub_rn(ay, ahh), ax2 = __fadd_rn(ax, ahw), ay2 = __fadd_rn(ay, ahh);
-    float best = 0.0f;
-    bool first = true;
+    const float area_a = __fmul_rn(aw, ah);
+    // max_n IoU > thr (:283-286) == "some IoU > thr and no IoU is NaN" (torch.max propagates NaN, and NaN > thr is False)
+    bool above = false, nan_seen = false;
     for (int t = 0; t < n; ++t) {
-        float v;
         if (csimple && tsimple[t]) {
-            const float bhw = __fmul_rn(tb[t][2], 0.5f), bhh = __fmul_rn(tb[t][3], 0.5f);
-            const float tlx = fmaxf(ax1, __fsub_rn(tb[t][0], bhw)), brx = fminf(ax2, __fadd_rn(tb[t][0], bhw));
-            const float tly = fmaxf(ay1, __fsub_rn(tb[t][1], bhh)), bry = fminf(ay2, __fadd_rn(tb[t][1], bhh));
-            v = (tlx < brx && tly < bry) ? iou_xywh(ax, ay, aw, ah, tb[t][0], tb[t][1], tb[t][2], tb[t][3]) : 0.0f;
+            const float4 g = *reinterpret_cast<const float4 *>(tc[t]);
+            const float tlx = fmaxf(ax1, g.x), brx = fminf(ax2, g.z);
+            const float tly = fmaxf(ay1, g.y), bry = fminf(ay2, g.w);
+            if (tlx < brx && tly < bry) {
+                // same operations as iou_xywh with en == 1; the quotient is only formed when the comparison is within
+                // 0.1 % of the threshold (its rounding error is 6e-8)
+                const float ai = __fmul_rn(__fsub_rn(brx, tlx), __fsub_rn(bry, tly));
+                const float uni = __fsub_rn(__fadd_rn(area_a, tarea[t]), ai);
+                const float tu = __fmul_rn(ignore_thre, uni);
+                bool d;
+                if (uni > 0.0f && uni < 3.0e38f && ai > 1.001f * tu && ai < 3.0e38f) d = true;
+                else if (uni > 0.0f && uni < 3.0e38f && ai < 0.999f * tu) d = false;
+                else d = __fdiv_rn(ai, uni) > ignore_thre;
+                above |= d;
+            }
         } else {
-            v = iou_xywh(ax, ay, aw, ah, tb[t][0], tb[t][1], tb[t][2], tb[t][3]);
+            const float v = iou_xywh(ax, ay, aw, ah, tb[t][0], tb[t][1], tb[t][2], tb[t][3]);
+            nan_seen |= (v != v);
+            above |= (v > ignore_thre);
         }
-        best = first ? v : nanmaxf(best, v);                          // torch.max propagates NaN (:283)
-        first = false;
     }
-    obj_mask[(size_t)b * cells + cell] = (best > ignore_thre) ? 0.0f : 1.0f;   // :286-294
+    const bool best_above = above && !nan_seen;
+    obj_mask[(size_t)b * cells + cell] = best_above ? 0.0f : 1.0f;             // :286-294
 }
 
 struct AnchorSet { float w[9], h[9]; int mask[3]; };
@@ -187,10 +234,6 @@ extern "C" int yl_build_target(const float *pred, const long *ps, const float *l
     if (B <= 0 || F <= 0 || K <= 0 || K > TG_MAXK || C <= 0 || layer_no < 0 || layer_no > 2) return YL_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     const float stride = (float)(8 << layer_no);                                              // yololoss.py:99,136
-    const size_t cells = (size_t)B * 3 * F * F;
-    YL_CUDA_TRY(cudaMemsetAsync(target, 0, sizeof(float) * cells * (5 + C), st));             // :156-167
-    YL_CUDA_TRY(cudaMemsetAsync(tgt_mask, 0, sizeof(float) * cells * (4 + C), st));
-    YL_CUDA_TRY(cudaMemsetAsync(tgt_scale, 0, sizeof(float) * cells * 2, st));
     if (status) YL_CUDA_TRY(cudaMemsetAsync(status, 0, sizeof(int), st));
     AnchorSet an;
     for (int q = 0; q < 9; ++q) {                                                             // :139-150
@@ -202,8 +245,8 @@ extern "C" int yl_build_target(const float *pred, const long *ps, const float *l
         an.mask[a] = anchor_mask3[a];
     }
     dim3 grid((3 * F * F + TG_THREADS - 1) / TG_THREADS, B);
-    k_target_objmask<<<grid, TG_THREADS, 0, st>>>(pred, ps[0], ps[1], ps[2], ps[3], ps[4], labels, F, K, stride, ignore_thre,
-                                                  obj_mask);
+    k_target_objmask<<<grid, TG_THREADS, 0, st>>>(pred, ps[0], ps[1], ps[2], ps[3], ps[4], labels, F, K, C, stride, ignore_thre,
+                                                  obj_mask, target, tgt_mask, tgt_scale);
     YL_LAUNCH_CHECK();
     k_target_scatter<<<B, TG_THREADS, 0, st>>>(labels, F, K, C, stride, an, target, obj_mask, tgt_mask, tgt_scale, status);
     YL_LAUNCH_CHECK();
