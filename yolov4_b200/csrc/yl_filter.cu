@@ -430,15 +430,17 @@ __device__ __forceinline__ void flag_tile(const RawParams &P, const RawLayer &Ly
     ldg_stream<VEC, NW>(P, Ly, ba, p0, true, obj, lth, bits);
     const int b = ba / 3, a = ba - 3 * b;
     const size_t r = (size_t)b * P.M4 + (Ly.row_off + a * Ly.F2 + p0);
+    // the emit kernel reads these 16 B per box right after this kernel: keep them in L2 while the raw stream passes through
     if (VEC == 4) {
-        *reinterpret_cast<float4 *>(P.objtab + r) = make_float4(obj[0], obj[1], obj[2], obj[3]);
+        stg_keep4(P.objtab + r, make_uint4(__float_as_uint(obj[0]), __float_as_uint(obj[1 % VEC]), __float_as_uint(obj[2 % VEC]),
+                                           __float_as_uint(obj[3 % VEC])));
 #pragma unroll
         for (int w = 0; w < NW; ++w)
-            *reinterpret_cast<uint4 *>(P.flags + (size_t)w * P.BM4 + r) = make_uint4(bits[0][w], bits[1][w], bits[2][w], bits[3][w]);
+            stg_keep4(P.flags + (size_t)w * P.BM4 + r, make_uint4(bits[0][w], bits[1 % VEC][w], bits[2 % VEC][w], bits[3 % VEC][w]));
     } else {
-        P.objtab[r] = obj[0];
+        stg_keep1(P.objtab + r, __float_as_uint(obj[0]));
 #pragma unroll
-        for (int w = 0; w < NW; ++w) P.flags[(size_t)w * P.BM4 + r] = bits[0][w];
+        for (int w = 0; w < NW; ++w) stg_keep1(P.flags + (size_t)w * P.BM4 + r, bits[0][w]);
     }
 }
 
@@ -853,9 +855,7 @@ k_filter_dense(const float *__restrict__ pred, long M, int C, int num_classes, f
                 v[q][j] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (i < nch && g0 + q < g_end) {
                     if (base4 + i < total4) {
-                        const float4 *src = p4 + base4 + i;
-                        asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-                                     : "=f"(v[q][j].x), "=f"(v[q][j].y), "=f"(v[q][j].z), "=f"(v[q][j].w) : "l"(src));
+                        v[q][j] = ldg_stream4(reinterpret_cast<const float *>(p4 + base4 + i));
                     } else if (base4 + i == total4) {
                         // the tensor ends inside this float4 (rows_total * (5+C) not a multiple of 4): scalar loads
                         const long rem = rows_total * nch - 4 * total4;

@@ -146,18 +146,18 @@ struct alignas(16) BinsSmem {
 // Number of keys below `key`; keys beyond n are padded with 0xFFFFFFFF up to a multiple of four.
 __device__ __forceinline__ int rank32(const unsigned *sh_key, int n, unsigned key)
 {
-    int r = 0;
+    int r0 = 0, r1 = 0, r2 = 0, r3 = 0;                        // four independent counters: no serial chain through the adds
     const uint4 *k4 = reinterpret_cast<const uint4 *>(sh_key);
     const int n4 = (n + 3) >> 2;
 #pragma unroll 4
     for (int j = 0; j < n4; ++j) {
         const uint4 k = k4[j];
         asm("{\n\t.reg .pred p, q, r, s;\n\t"
-            "setp.lt.u32 p, %1, %5;\n\tsetp.lt.u32 q, %2, %5;\n\tsetp.lt.u32 r, %3, %5;\n\tsetp.lt.u32 s, %4, %5;\n\t"
-            "@p add.s32 %0, %0, 1;\n\t@q add.s32 %0, %0, 1;\n\t@r add.s32 %0, %0, 1;\n\t@s add.s32 %0, %0, 1;\n\t}"
-            : "+r"(r) : "r"(k.x), "r"(k.y), "r"(k.z), "r"(k.w), "r"(key));
+            "setp.lt.u32 p, %4, %8;\n\tsetp.lt.u32 q, %5, %8;\n\tsetp.lt.u32 r, %6, %8;\n\tsetp.lt.u32 s, %7, %8;\n\t"
+            "@p add.s32 %0, %0, 1;\n\t@q add.s32 %1, %1, 1;\n\t@r add.s32 %2, %2, 1;\n\t@s add.s32 %3, %3, 1;\n\t}"
+            : "+r"(r0), "+r"(r1), "+r"(r2), "+r"(r3) : "r"(k.x), "r"(k.y), "r"(k.z), "r"(k.w), "r"(key));
     }
-    return r;
+    return (r0 + r1) + (r2 + r3);
 }
 
 // Number of keys below `key` (keys are unique): LDS.128 per two keys, one 64-bit compare + predicated add per key.
@@ -692,7 +692,15 @@ k_gather_rows(const uint4 *__restrict__ cand, const unsigned *__restrict__ seg_c
     const unsigned nwr = (unsigned)min((long)nk, max(0L, cap_out - (long)pre));      // rows that fit the output capacity
     const float *src = reinterpret_cast<const float *>(cand + (size_t)seg * cap_seg * 2);
     float *dst = out_rows + ((size_t)b * cap_out + pre) * 7;
-    for (unsigned i = tid; i < nwr * 7u; i += GATHER_THREADS) dst[i] = src[i];
+    // the source run is 16-byte aligned, the destination only 4-byte: 128-bit loads, scalar stores
+    const unsigned nf = nwr * 7u, nf4 = nf >> 2;
+    const float4 *src4 = reinterpret_cast<const float4 *>(src);
+    for (unsigned i = tid; i < nf4; i += GATHER_THREADS) {
+        const float4 v = src4[i];
+        float *d = dst + 4 * i;
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    }
+    if (tid < (nf & 3u)) dst[4 * nf4 + tid] = src[4 * nf4 + tid];
 }
 
 // Smallest K such that two positive areas whose bins (float bits >> 21: four per octave) differ by at least K have a
