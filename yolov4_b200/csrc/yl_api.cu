@@ -28,7 +28,8 @@ extern "C" const char *yl_error_string(int code)
 
 // -------------------------------------------------------------------------------------------------------------
 // Host-buffer path.  Images are independent (utils.py:133), so the batch is cut into groups: group g's H2D copy
-// runs on the copy stream while group g-1 is filtered and suppressed on the compute stream.
+// runs on the copy stream while group g-1 is filtered and suppressed on the compute stream and the kept rows of
+// group g-2 travel back on a third stream (PCIe is full duplex), so only the last group's results trail the uploads.
 // -------------------------------------------------------------------------------------------------------------
 struct yl_context {
     int device, B, n_layers, C, cap_seg, n_groups;
@@ -42,8 +43,8 @@ struct yl_context {
     float *d_rows;
     int *d_meta;
     int *h_meta;                   // pinned
-    cudaStream_t s_copy, s_comp;
-    cudaEvent_t ev_copied[16], ev_done;
+    cudaStream_t s_copy, s_comp, s_back;
+    cudaEvent_t ev_copied[16], ev_meta[16], ev_done;
 };
 
 extern "C" int yl_context_destroy(yl_context *c)
@@ -56,6 +57,8 @@ extern "C" int yl_context_destroy(yl_context *c)
     if (c->d_meta) cudaFree(c->d_meta);
     if (c->h_meta) cudaFreeHost(c->h_meta);
     for (int g = 0; g < 16; ++g) if (c->ev_copied[g]) cudaEventDestroy(c->ev_copied[g]);
+    for (int g = 0; g < 16; ++g) if (c->ev_meta[g]) cudaEventDestroy(c->ev_meta[g]);
+    if (c->s_back) cudaStreamDestroy(c->s_back);
     if (c->ev_done) cudaEventDestroy(c->ev_done);
     if (c->s_copy) cudaStreamDestroy(c->s_copy);
     if (c->s_comp) cudaStreamDestroy(c->s_comp);
@@ -89,7 +92,9 @@ extern "C" int yl_context_create(yl_context **out, int device, int B, const int 
     CTX_TRY(cudaMallocHost(&c->h_meta, sizeof(int) * 3 * (size_t)B));
     CTX_TRY(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
     CTX_TRY(cudaStreamCreateWithFlags(&c->s_comp, cudaStreamNonBlocking));
+    CTX_TRY(cudaStreamCreateWithFlags(&c->s_back, cudaStreamNonBlocking));
     for (int g = 0; g < c->n_groups; ++g) CTX_TRY(cudaEventCreateWithFlags(&c->ev_copied[g], cudaEventDisableTiming));
+    for (int g = 0; g < c->n_groups; ++g) CTX_TRY(cudaEventCreateWithFlags(&c->ev_meta[g], cudaEventDisableTiming));
     CTX_TRY(cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming));
 #undef CTX_TRY
     *out = c;
@@ -122,17 +127,29 @@ extern "C" int yl_detect_host(yl_context *c, const float *const *raw_host, float
         if (rc != YL_OK) return rc;
         rc = yl_nms(c->ws, c->ws_bytes, B, c->M, C, c->cap_seg, nms_thre, c->d_rows, c->cap_out, c->d_meta, i0, i1 - i0, c->s_comp);
         if (rc != YL_OK) return rc;
+        // this group's three meta slices (kept rows, largest segment, candidate total) follow the kernels
+        for (int k = 0; k < 3; ++k)
+            YL_CUDA_TRY(cudaMemcpyAsync(c->h_meta + (size_t)k * B + i0, c->d_meta + (size_t)k * B + i0, sizeof(int) * (size_t)(i1 - i0),
+                                        cudaMemcpyDeviceToHost, c->s_comp));
+        YL_CUDA_TRY(cudaEventRecord(c->ev_meta[g], c->s_comp));
     }
-    YL_CUDA_TRY(cudaMemcpyAsync(c->h_meta, c->d_meta, sizeof(int) * 3 * (size_t)B, cudaMemcpyDeviceToHost, c->s_comp));
-    YL_CUDA_TRY(cudaStreamSynchronize(c->s_comp));
-    for (int b = 0; b < B; ++b) {
-        if (c->h_meta[B + b] > c->cap_seg) return YL_ERR_CAPACITY;
-        counts_host[b] = c->h_meta[b];
-        const long k = c->h_meta[b] < c->cap_out ? c->h_meta[b] : c->cap_out;
-        if (k > 0)
-            YL_CUDA_TRY(cudaMemcpyAsync(out_rows_host + (size_t)b * c->cap_out * 7, c->d_rows + (size_t)b * c->cap_out * 7,
-                                        sizeof(float) * 7 * (size_t)k, cudaMemcpyDeviceToHost, c->s_comp));
+    // everything above is enqueued; the host now follows the groups and sends each one's kept rows back while the
+    // uploads of the later groups are still running
+    int status = YL_OK;
+    for (int g = 0; g < G; ++g) {
+        const int i0 = (int)((long)B * g / G), i1 = (int)((long)B * (g + 1) / G);
+        if (i1 == i0) continue;
+        YL_CUDA_TRY(cudaEventSynchronize(c->ev_meta[g]));
+        for (int b = i0; b < i1; ++b) {
+            if (c->h_meta[B + b] > c->cap_seg) status = YL_ERR_CAPACITY;
+            counts_host[b] = c->h_meta[b];
+            const long k = c->h_meta[b] < c->cap_out ? c->h_meta[b] : c->cap_out;
+            if (k > 0 && status == YL_OK)
+                YL_CUDA_TRY(cudaMemcpyAsync(out_rows_host + (size_t)b * c->cap_out * 7, c->d_rows + (size_t)b * c->cap_out * 7,
+                                            sizeof(float) * 7 * (size_t)k, cudaMemcpyDeviceToHost, c->s_back));
+        }
     }
+    YL_CUDA_TRY(cudaStreamSynchronize(c->s_back));
     YL_CUDA_TRY(cudaStreamSynchronize(c->s_comp));
-    return YL_OK;
+    return status;
 }

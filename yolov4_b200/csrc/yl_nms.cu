@@ -104,9 +104,12 @@ __device__ __forceinline__ void store_row(float *o, const float4 &box, unsigned 
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int SMALL_R = 256;
 constexpr int SMALL_W = SMALL_R / 32;
-constexpr int SMALL_THREADS = 128;
+#ifndef YL_NMS_THREADS
+#define YL_NMS_THREADS 128
+#endif
+constexpr int SMALL_THREADS = YL_NMS_THREADS;          // a multiple of 32
 constexpr int SMALL_WARPS = SMALL_THREADS / 32;
-constexpr int SMALL_EPT = SMALL_R / SMALL_THREADS;      // records per thread, at most
+constexpr int SMALL_EPT = (SMALL_R + SMALL_THREADS - 1) / SMALL_THREADS;      // records per thread, at most
 #ifndef YL_NMS_NBIN
 #define YL_NMS_NBIN 48
 #endif
@@ -285,8 +288,9 @@ k_segment_nms_bins(uint4 *__restrict__ cand, const unsigned *__restrict__ seg_co
 
     // ---- 3. sorted arrays, bins, table inserts ----
     {
-        lo = fminf(fminf(S.red[0][0], S.red[0][1]), fminf(S.red[0][2], S.red[0][3]));
-        hi = fmaxf(fmaxf(S.red[1][0], S.red[1][1]), fmaxf(S.red[1][2], S.red[1][3]));
+        lo = S.red[0][0]; hi = S.red[1][0];
+#pragma unroll
+        for (int wq = 1; wq < SMALL_WARPS; ++wq) { lo = fminf(lo, S.red[0][wq]); hi = fmaxf(hi, S.red[1][wq]); }
         lo = fmaxf(lo, -1.0e6f);
         hi = fminf(hi, 1.0e6f);
         float scale = __fdiv_rn((float)NBIN, __fsub_rn(hi, lo));
@@ -385,7 +389,9 @@ k_segment_nms_bins(uint4 *__restrict__ cand, const unsigned *__restrict__ seg_co
         if (tid == 0) big_list[atomicAdd(big_count, 1u)] = (unsigned)seg;
         return;
     }
-    const unsigned qtotal = S.qn[0] + S.qn[1] + S.qn[2] + S.qn[3];
+    unsigned qtotal = 0u;
+#pragma unroll
+    for (int wq = 0; wq < SMALL_WARPS; ++wq) qtotal += S.qn[wq];
 
     // ---- 5. exact tests on the queued pairs, suppression matrix, resolve ----
     bool any_edges = false;
