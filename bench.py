@@ -143,6 +143,9 @@ def main():
         run_reference(args, rank, world)
         return
     args.warmup = max(args.warmup, 3)
+    # stdout carries exactly one JSON line: keep NCCL's version banner off it
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
 
     import torch
     import torch.distributed as dist
