@@ -141,6 +141,27 @@ int yl_coco_rows(const float *rows, const int *row_image, long K, const double *
                  const int *class_ids, int n_classes, int mode, double *out, yl_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * N2  YOLOLoss.forward for one layer, fused            replaces yolo/model/yololoss.py:390-432
+ *                    (with the train-mode YOLOLayer, yololayer.py:122-145, and build_target, :118-371, it consumes)
+ *   raw        [B, 3*(5+C), F, F] raw head tensor of the layer (device fp32)
+ *   labels     [B,K,5] fp32 as for yl_build_target
+ *   loss4      device float64[4], ACCUMULATED into: loss_xy (:421), loss_wh (:423), loss_obj (:425), loss_cls (:427);
+ *              the layer's loss is their sum (:432); zero it before the first layer
+ *   saved for yl_loss_backward: gobj [B,3,F,F] fp32 (d loss / d raw objectness), tcell_all / mcell int32 [B,K],
+ *              mgrad [B,K,4+C] fp32 (d loss / d raw xy,wh,classes of the matched cells)
+ *   status     device int32[1] (caller zeroes it), set non-zero when a matched GT indexes outside the grid or carries a
+ *              class id outside [0, C) (the reference raises IndexError / writes another channel there); may be NULL
+ * yl_loss_backward: grad_raw [B, 3*(5+C), F, F] = upstream[0] * d loss / d raw (upstream: device fp32 scalar).
+ * None of the reference's dense output / pred / target / mask tensors is materialised: 5 of the 5+C planes are read.
+ * --------------------------------------------------------------------------------------------------------- */
+int yl_loss_forward(const float *raw, const float *labels, int B, int F, int K, int C, int layer_no,
+                    const float *anchors_px, const int *anchor_mask3, float ignore_thre,
+                    double *loss4, float *gobj, int *tcell_all, int *mcell, float *mgrad, int *status,
+                    yl_stream_t stream);
+int yl_loss_backward(const float *gobj, const int *mcell, const float *mgrad, const float *upstream,
+                     int B, int F, int K, int C, float *grad_raw, yl_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * Host-buffer entry (what a non-Python caller binds; also the bench's end-to-end leg): raw head tensors in
  * HOST memory -> detections in HOST memory.  The context owns device staging buffers, workspace, streams and
  * pinned bounce buffers; H2D copies, kernels and the D2H of rows/counts are all inside the call.

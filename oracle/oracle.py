@@ -205,3 +205,64 @@ def build_target(pred, labels, layer_no, n_classes=80, ignore_thre=0.7, anchors=
     if rc != 0:
         raise IndexError("a matched GT indexes outside the grid (reference: IndexError at yololoss.py:330)")
     return target, obj_mask, tgt_mask, tgt_scale
+
+
+def yolo_loss_layer(raw, labels, layer_no, n_classes=80, ignore_thre=0.7, anchors=ANCHORS_PX, mask=ANCHOR_MASK):
+    """N2: one layer of YOLOLoss.forward (yolo/model/yololoss.py:390-432) starting from the raw head tensor.
+
+    raw [B,3*(5+C),F,F] -> train-mode YOLOLayer (decode_train, yololayer.py:122-145) -> build_target (:118-371) -> the masked
+    BCE / MSE sums of :402-432.  Returns (losses = float64 [xy, wh, obj, cls], grad_raw [B,3*(5+C),F,F] float64), the gradient
+    of their sum with respect to raw: ATen's binary_cross_entropy_backward ((x - t) / max((1 - x) x, 1e-12) * weight),
+    mse_loss_backward (2 (a - b)), the in-place mask multiplications of :402-407 and sigmoid' on the xy / obj / cls channels.
+    numpy restatement (float32 values, float64 accumulation); the mask / target logic is the C oracle's."""
+    raw = np.ascontiguousarray(raw, dtype=np.float32)
+    B, _, F, _ = raw.shape
+    nch = 5 + n_classes
+    output, pred = decode_train(raw, layer_no, n_classes, anchors, mask)             # [B,3,F,F,nch], [B,3,F,F,4]
+    target, obj_mask, tgt_mask, tgt_scale = build_target(pred, np.asarray(labels, np.float32), layer_no, n_classes, ignore_thre,
+                                                         anchors, mask)
+    sel = np.r_[0:4, 5:nch]
+    out_m = np.array(output, dtype=np.float32)                                       # :402-407 (float32 products, in this order)
+    out_m[..., 4] = out_m[..., 4] * obj_mask
+    out_m[..., sel] = out_m[..., sel] * tgt_mask
+    out_m[..., 2:4] = out_m[..., 2:4] * tgt_scale
+    tgt = np.array(target, dtype=np.float32)                                         # :411-413
+    tgt[..., 4] = tgt[..., 4] * obj_mask
+    tgt[..., sel] = tgt[..., sel] * tgt_mask
+    tgt[..., 2:4] = tgt[..., 2:4] * tgt_scale
+
+    def bce(x, t, w=None):                                                           # ATen binary_cross_entropy, reduction sum
+        with np.errstate(divide="ignore"):
+            lx = np.maximum(np.log(x.astype(np.float32)), np.float32(-100.0)).astype(np.float64)
+            l1x = np.maximum(np.log((np.float32(1.0) - x).astype(np.float32)), np.float32(-100.0)).astype(np.float64)
+        v = (t.astype(np.float64) - 1.0) * l1x - t.astype(np.float64) * lx
+        if w is not None:
+            v = v * w.astype(np.float64)
+        return v
+
+    def bce_grad(x, t, w=None):
+        x64, t64 = x.astype(np.float64), t.astype(np.float64)
+        g = (x64 - t64) / np.maximum((1.0 - x64) * x64, 1e-12)
+        return g * w.astype(np.float64) if w is not None else g
+
+    w_xy = (tgt_scale * tgt_scale).astype(np.float32)                                # :417
+    losses = np.array([
+        bce(out_m[..., :2], tgt[..., :2], w_xy).sum(),                               # :421
+        (np.square(out_m[..., 2:4].astype(np.float64) - tgt[..., 2:4].astype(np.float64))).sum() / 2.0,   # :423
+        bce(out_m[..., 4], tgt[..., 4]).sum(),                                       # :425
+        bce(out_m[..., 5:], tgt[..., 5:]).sum(),                                     # :427
+    ], dtype=np.float64)
+    g_m = np.zeros(out_m.shape, np.float64)                                          # d loss / d out_m
+    g_m[..., :2] = bce_grad(out_m[..., :2], tgt[..., :2], w_xy)
+    g_m[..., 2:4] = out_m[..., 2:4].astype(np.float64) - tgt[..., 2:4].astype(np.float64)
+    g_m[..., 4] = bce_grad(out_m[..., 4], tgt[..., 4])
+    g_m[..., 5:] = bce_grad(out_m[..., 5:], tgt[..., 5:])
+    g_o = np.array(g_m)                                                              # back through the mask products
+    g_o[..., 2:4] = g_o[..., 2:4] * tgt_scale
+    g_o[..., sel] = g_o[..., sel] * tgt_mask
+    g_o[..., 4] = g_o[..., 4] * obj_mask
+    o64 = np.asarray(output, np.float64)                                             # sigmoid' on xy / obj / cls, identity on wh
+    dsig = o64 * (1.0 - o64)
+    dsig[..., 2:4] = 1.0
+    g_raw = (g_o * dsig).transpose(0, 1, 4, 2, 3).reshape(B, 3 * nch, F, F)
+    return losses, g_raw

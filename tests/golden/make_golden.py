@@ -269,11 +269,69 @@ def gen_epilogue():
     print("epilogue.npz", out["coco"].shape, out["detect"].shape)
 
 
+def gen_loss():
+    """N2: YOLOLoss.forward (yololoss.py:373-443) on the three train-mode YOLOLayer outputs, and its gradient with respect
+    to the raw head tensors by the reference's own autograd.  Some raw cells are planted so that their decoded box
+    coincides with a ground truth (ignore mask zeros, yololoss.py:276-294); labels include same-cell collisions."""
+    img, C, B, K = 96, 20, 4, 60
+    raws = [r.clone() for r in synth_head_outputs(B, img, C, seed=21, fg_prob=0.05)]
+    rng = np.random.RandomState(31)
+    labels = np.zeros((B, K, 5), np.float64)
+
+    def rand_gt(n, wmax):
+        wh = rng.rand(n, 2) * wmax + 4
+        xy = rng.rand(n, 2) * (img - 2) + 1
+        cls = rng.randint(0, C, size=(n, 1))
+        return np.concatenate([xy, wh, cls], 1)
+
+    labels[0, :10] = rand_gt(10, 80)
+    g = rand_gt(6, 50)
+    g[1, :4] = g[0, :4]; g[1, 4] = (g[0, 4] + 1) % C        # same box, other class: one-hots accumulate
+    g[2, :2] = g[0, :2] + 0.25; g[2, 2:4] = g[0, 2:4] * 1.02  # same cell: last writer wins on xy / wh / scale
+    labels[1, :6] = g
+    # image 2: no labels
+    labels[3, :14] = rand_gt(14, 30)
+    nch = 5 + C
+    for l in range(3):                                       # plant predictions on top of ground truths
+        s = 8 << l
+        F = img // s
+        for b in range(B):
+            for t in range(K):
+                if labels[b, t].sum() > 0 and rng.rand() < 0.6:
+                    gx, gy, gw, gh = labels[b, t, :4] / s
+                    i, j = min(int(gx), F - 1), min(int(gy), F - 1)
+                    a = rng.randint(0, 3)
+                    aw, ah = ANCHORS[MASK[l][a]][0] / s, ANCHORS[MASK[l][a]][1] / s
+                    fx, fy = min(max(gx - i, 0.02), 0.98), min(max(gy - j, 0.02), 0.98)
+                    raws[l][b, a * nch + 0, j, i] = float(np.log(fx / (1 - fx)))
+                    raws[l][b, a * nch + 1, j, i] = float(np.log(fy / (1 - fy)))
+                    raws[l][b, a * nch + 2, j, i] = float(np.log(gw / aw))
+                    raws[l][b, a * nch + 3, j, i] = float(np.log(gh / ah))
+    out = {"labels": labels.astype(np.float32), "img": np.int32(img), "C": np.int32(C)}
+    crit = YOLOLoss(cfg(C), ignore_thresh=0.7, device="cpu")
+    leaves = [r.clone().requires_grad_(True) for r in raws]
+    # the reference layer works in place on (a view of) its input, which in the model is a conv output, not a leaf
+    outs = [YOLOLayer(cfg(C), l, device="cpu").train()(leaves[l] * 1.0) for l in range(3)]
+    total = crit(outs, {"padded_labels": torch.from_numpy(labels)})
+    total.backward()
+    out["loss"] = np.float64(total.item())
+    for l in range(3):
+        out[f"raw{l}"] = raws[l].numpy()
+        out[f"grad{l}"] = leaves[l].grad.numpy()
+        # per-layer value (fresh graph: the reference's forward overwrites `output` in place)
+        leaf = raws[l].clone()
+        with torch.no_grad():
+            d = YOLOLayer(cfg(C), l, device="cpu").train()(leaf)
+            out[f"loss{l}"] = np.float64(crit([d], {"padded_labels": torch.from_numpy(labels)}).item())
+    print("loss", out["loss"], [out[f"loss{l}"] for l in range(3)])
+    np.savez_compressed(os.path.join(HERE, "loss.npz"), **out)
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     only = sys.argv[1:]
     for name, fn in (("decode", gen_decode), ("postprocess", gen_postprocess), ("nms", gen_nms), ("iou", gen_iou),
-                     ("build_target", gen_build_target), ("epilogue", gen_epilogue)):
+                     ("build_target", gen_build_target), ("epilogue", gen_epilogue), ("loss", gen_loss)):
         if not only or name in only:
             fn()
     for f in sorted(os.listdir(HERE)):

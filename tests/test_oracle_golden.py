@@ -158,3 +158,19 @@ def test_spec_math_accuracy():
     assert np.isnan(orc.expf(np.float32("nan")))
     assert orc.expf(np.float32(100.0)) == np.inf and orc.expf(np.float32(-200.0)) == 0.0
     assert orc.sigmoidf(np.float32(0.0)) == np.float32(0.5)
+
+
+def test_loss_oracle_vs_reference_forward_and_autograd(golden_dir):
+    """N2: the oracle's restatement of YOLOLoss.forward (yololoss.py:390-432) against the reference's loss value and the
+    gradient its autograd produces with respect to the raw head tensors."""
+    g = _load(golden_dir, "loss.npz")
+    C = int(g["C"])
+    total = 0.0
+    for l in range(3):
+        losses, grad = orc.yolo_loss_layer(g[f"raw{l}"], g["labels"], l, C, 0.7)
+        assert abs(losses.sum() - float(g[f"loss{l}"])) <= 1e-5 * abs(float(g[f"loss{l}"])), (l, losses, float(g[f"loss{l}"]))
+        ref = g[f"grad{l}"].astype(np.float64)
+        assert np.array_equal(grad != 0, ref != 0), "layer %d: gradient support differs" % l
+        assert np.allclose(grad, ref, rtol=2e-5, atol=1e-7), (l, np.abs(grad - ref).max())
+        total += losses.sum()
+    assert abs(total - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))

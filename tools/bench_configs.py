@@ -77,3 +77,20 @@ bytes_bt = 64 * 16.01e6
 print("  %.1f us/step  %.0f img/s  %.0f GB/s of dense outputs (eager, incl. allocation of 1 GB of outputs)" % (us, 64 / us * 1e6, bytes_bt / us / 1e3))
 us_dt = timeit(lambda: [yb.YOLOLayer(CFG, l, device="cuda").train()(raws[l]) for l in range(3)])
 print("  train-mode YOLOLayer.forward x3: %.1f us (%.0f GB/s r+w)" % (us_dt, 2 * 64 * BPI / us_dt / 1e3))
+
+print("N2: fused YOLO loss (raw head tensors -> loss -> grad_raw), B=64 @608, 50 GT/image, all three layers")
+raws_g = [r.clone().requires_grad_(True) for r in raws]
+def fused_fb():
+    for r in raws_g:
+        r.grad = None
+    yb.fused_yolo_loss(raws_g, labels, CFG, 0.7).backward()
+us_f = timeit(lambda: yb.fused_yolo_loss_components(raws, labels, CFG, 0.7))
+us_fb = timeit(fused_fb)
+def unfused_fb():
+    for r in raws_g:
+        r.grad = None
+    outs_ = [yb.YOLOLayer(CFG, l, device="cuda").train()(raws_g[l]) for l in range(3)]
+    crit(outs_, {"padded_labels": labels.double()}).backward()
+us_ufb = timeit(unfused_fb, n=5, warm=2)
+print("  fused forward %.1f us; fused forward+backward %.1f us (eager, CUDA events); unfused CUDA path "
+      "(YOLOLayer.train + build_target + torch loss arithmetic + autograd) %.1f us" % (us_f, us_fb, us_ufb))

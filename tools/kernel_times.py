@@ -25,3 +25,7 @@ raws3 = synth_head_outputs(256, 608, 80, seed=1, device="cuda")
 for _ in range(3):
     yb.detect_raw(raws3, 80, 0.2, 0.5)                                     # config 3
 torch.cuda.synchronize()
+raws_g = [r.clone().requires_grad_(True) for r in raws]
+for _ in range(3):
+    yb.fused_yolo_loss(raws_g, labels, CFG, 0.7).backward()                 # N2
+torch.cuda.synchronize()

@@ -56,6 +56,10 @@ def lib():
     L.yl_build_target.argtypes = [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _f, _p, _p, _p, _p, _p, _p]
     L.yl_coco_rows.restype = _i
     L.yl_coco_rows.argtypes = [_p, _p, _l, _p, _p, _p, _i, _i, _p, _p]
+    L.yl_loss_forward.restype = _i
+    L.yl_loss_forward.argtypes = [_p, _p, _i, _i, _i, _i, _i, _p, _p, _f, _p, _p, _p, _p, _p, _p, _p]
+    L.yl_loss_backward.restype = _i
+    L.yl_loss_backward.argtypes = [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p]
     L.yl_context_create.restype = _i
     L.yl_context_create.argtypes = [ctypes.POINTER(_p), _i, _i, _p, _i, _i, _p, _p, _i, _l]
     L.yl_context_destroy.restype = _i
@@ -71,6 +75,7 @@ def lib():
 EXPORTS = [
     "yl_abi_version", "yl_error_string", "yl_decode_dense", "yl_decode_train", "yl_decode_train_backward",
     "yl_post_workspace_bytes", "yl_post_reset", "yl_filter_raw", "yl_filter_raw_stage", "yl_filter_dense", "yl_nms", "yl_build_target", "yl_coco_rows",
+    "yl_loss_forward", "yl_loss_backward",
     "yl_context_create", "yl_context_destroy", "yl_detect_host",
 ]
 

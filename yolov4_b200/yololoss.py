@@ -93,3 +93,88 @@ class YOLOLoss(nn.Module):
             loss_cls = self.bce_loss(out_m[..., 5:], target[..., 5:])
             total = total + loss_xy + loss_wh + loss_obj + loss_cls
         return total
+
+
+class _FusedYoloLoss(torch.autograd.Function):
+    """N2: raw head tensors + padded labels -> the reference's YOLOLoss.forward value, gradient straight to the raw tensors."""
+
+    @staticmethod
+    def forward(ctx, labels, anchors, anchor_mask, ignore_thresh, n_classes, *raws):
+        L = _cabi.lib()
+        dev = raws[0].device
+        lab = labels.to(device=dev, dtype=torch.float32).contiguous()
+        B, K = int(lab.shape[0]), int(lab.shape[1])
+        C = int(n_classes)
+        loss4 = torch.zeros(4, dtype=torch.float64, device=dev)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        anch = _cabi.floats([v for wh in anchors for v in wh])
+        saved = []
+        with torch.cuda.device(dev):
+            for l, r in enumerate(raws):
+                if not r.is_cuda or r.dtype != torch.float32 or r.dim() != 4 or r.shape[1] != 3 * (5 + C) or r.shape[0] != B:
+                    raise TypeError("fused YOLO loss needs float32 CUDA head tensors [B, 3*(5+C), F, F]; there is no CPU fallback")
+                rc = r.detach().contiguous()
+                F = int(rc.shape[2])
+                gobj = torch.empty((B, 3, F, F), dtype=torch.float32, device=dev)
+                tcell = torch.empty((B, K), dtype=torch.int32, device=dev)
+                mcell = torch.empty((B, K), dtype=torch.int32, device=dev)
+                mgrad = torch.empty((B, K, 4 + C), dtype=torch.float32, device=dev)
+                _cabi.check(L.yl_loss_forward(rc.data_ptr(), lab.data_ptr(), B, F, K, C, l, anch, _cabi.ints(anchor_mask[l]),
+                                              float(np.float32(ignore_thresh)), loss4.data_ptr(), gobj.data_ptr(), tcell.data_ptr(),
+                                              mcell.data_ptr(), mgrad.data_ptr(), status.data_ptr(), _stream()))
+                saved += [gobj, mcell, mgrad]
+        ctx.save_for_backward(*saved)
+        ctx.shapes = [tuple(r.shape) for r in raws]
+        ctx.K, ctx.C = K, C
+        ctx.status = status
+        ctx.loss4 = loss4
+        return loss4.sum().to(torch.float32)          # the reference returns a float32 scalar
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        L = _cabi.lib()
+        saved = ctx.saved_tensors
+        up = grad_out.detach().to(torch.float32).reshape(1).contiguous()
+        grads = []
+        with torch.cuda.device(up.device):
+            for l, shp in enumerate(ctx.shapes):
+                gobj, mcell, mgrad = saved[3 * l:3 * l + 3]
+                B, _, F, _ = shp
+                g = torch.empty(shp, dtype=torch.float32, device=up.device)
+                _cabi.check(L.yl_loss_backward(gobj.data_ptr(), mcell.data_ptr(), mgrad.data_ptr(), up.data_ptr(), B, F, ctx.K, ctx.C,
+                                               g.data_ptr(), _stream()))
+                grads.append(g)
+        return (None, None, None, None, None) + tuple(grads)
+
+
+def fused_yolo_loss(head_outputs, padded_labels, cfg, ignore_thresh=0.7):
+    """N2: the value of `YOLOLoss(cfg, ignore_thresh)([YOLOLayer_l.train()(x_l)], {'padded_labels': labels})`
+    (yolo/model/yololoss.py:373-443 on top of yololayer.py:122-145) computed from the three raw head tensors without
+    materialising output / pred / target / masks; differentiable with respect to the head tensors.
+    Loss and gradient agree with the reference within 1e-5 / 2e-5 relative (not bit-exact: reduction order)."""
+    return _FusedYoloLoss.apply(padded_labels, cfg['ANCHORS'], cfg['ANCHOR_MASK'], ignore_thresh, cfg['N_CLASSES'], *head_outputs)
+
+
+def fused_yolo_loss_components(head_outputs, padded_labels, cfg, ignore_thresh=0.7, layers=None):
+    """The four sums (loss_xy, loss_wh, loss_obj, loss_cls; yololoss.py:421-427) over the given layers as a float64[4] device
+    tensor, no autograd.  `layers[i]` is the layer number of head_outputs[i] (default 0, 1, 2)."""
+    L = _cabi.lib()
+    dev = head_outputs[0].device
+    lab = padded_labels.to(device=dev, dtype=torch.float32).contiguous()
+    B, K = int(lab.shape[0]), int(lab.shape[1])
+    C = int(cfg['N_CLASSES'])
+    loss4 = torch.zeros(4, dtype=torch.float64, device=dev)
+    anch = _cabi.floats([v for wh in cfg['ANCHORS'] for v in wh])
+    layers = list(range(len(head_outputs))) if layers is None else layers
+    with torch.cuda.device(dev):
+        for l, r in zip(layers, head_outputs):
+            rc = r.detach().contiguous()
+            F = int(rc.shape[2])
+            gobj = torch.empty((B, 3, F, F), dtype=torch.float32, device=dev)
+            tcell = torch.empty((B, K), dtype=torch.int32, device=dev)
+            mcell = torch.empty((B, K), dtype=torch.int32, device=dev)
+            mgrad = torch.empty((B, K, 4 + C), dtype=torch.float32, device=dev)
+            _cabi.check(L.yl_loss_forward(rc.data_ptr(), lab.data_ptr(), B, F, K, C, int(l), anch, _cabi.ints(cfg['ANCHOR_MASK'][l]),
+                                          float(np.float32(ignore_thresh)), loss4.data_ptr(), gobj.data_ptr(), tcell.data_ptr(),
+                                          mcell.data_ptr(), mgrad.data_ptr(), None, _stream()))
+    return loss4
