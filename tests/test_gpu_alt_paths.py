@@ -1,5 +1,5 @@
-"""Every selectable kernel form must give the oracle's answer bit for bit: the default split filter + block NMS, the fused
-TMA pipeline, the fused register-staged filter, and the warp-per-segment NMS tier."""
+"""Every selectable kernel form must give the oracle's answer bit for bit: the default split filter, the fused TMA pipeline
+and the fused register-staged filter."""
 import os
 import subprocess
 import sys
@@ -10,8 +10,8 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-@pytest.mark.parametrize("env", [{}, {"YL_FILTER": "fused"}, {"YL_FILTER": "fused", "YL_NO_TMA": "1"}, {"YL_NMS_WARP": "1"}],
-                         ids=["default", "fused-tma", "fused-ldg", "warp-nms"])
+@pytest.mark.parametrize("env", [{}, {"YL_FILTER": "fused"}, {"YL_FILTER": "fused", "YL_NO_TMA": "1"}],
+                         ids=["default", "fused-tma", "fused-ldg"])
 def test_kernel_forms_match_oracle(env):
     e = dict(os.environ)
     e.update(env)
