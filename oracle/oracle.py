@@ -10,6 +10,9 @@ Every wrapper takes/returns numpy arrays (fp32, C-contiguous) and mirrors one re
   postprocess      postprocess                  yolo/util/utils.py:92-223
   bboxes_iou       bboxes_iou                   yolo/model/yololoss.py:16-91
   build_target     YOLOLoss.build_target        yolo/model/yololoss.py:118-371
+  yolo_loss_layer  YOLOLoss.forward, one layer  yolo/model/yololoss.py:390-432  (numpy on top of decode_train + build_target;
+                   pinned to the reference's loss value and autograd gradient, tests/golden/loss.npz)
+  detect           decode_eval x3 + cat + postprocess (the composition the parity tests and the CPU baseline use)
 """
 import ctypes
 import os
