@@ -451,6 +451,7 @@ template <int NW>
 __global__ void __launch_bounds__(K1_THREADS, YL_FLAG_MINB)
 k_flag_raw(const __grid_constant__ RawParams P)
 {
+    pdl_trigger();
     const int ba = P.img_first * 3 + blockIdx.y;
     int tile = blockIdx.x;
     int l = 0;
@@ -506,6 +507,8 @@ __global__ void __launch_bounds__(K1_THREADS, YL_EMIT_MINB)
 k_emit_flagged(const __grid_constant__ RawParams P)
 {
     __shared__ LdgSmem sm;
+    pdl_trigger();
+    pdl_wait();                                                      // the flag words / sigmoid(obj) of k_flag_raw
     // Reverse order of k_flag_raw: the planes that kernel streamed last are still in L2 (126 MB of the 495 MB), so the
     // flagged logits / box planes of the first tiles handled here are re-read from L2 instead of DRAM.
     const int ba = P.img_first * 3 + ((int)gridDim.y - 1 - (int)blockIdx.y);
@@ -1082,12 +1085,15 @@ static int filter_raw_impl(const float *const *raw, const int *F, int n_layers, 
                 YL_LAUNCH_CHECK();
             }
             if (stages & 2) {
+                const bool pdl = pdl_enabled() && (stages & 1);             // directly behind k_flag_raw on the stream
+                cudaError_t le;
                 switch (NW) {
-                case 1: k_emit_flagged<1><<<grid, K1_THREADS, 0, st>>>(Pl); break;
-                case 2: k_emit_flagged<2><<<grid, K1_THREADS, 0, st>>>(Pl); break;
-                case 3: k_emit_flagged<3><<<grid, K1_THREADS, 0, st>>>(Pl); break;
-                default: k_emit_flagged<4><<<grid, K1_THREADS, 0, st>>>(Pl); break;
+                case 1: le = launch_after(k_emit_flagged<1>, grid, dim3(K1_THREADS), 0, st, pdl, Pl); break;
+                case 2: le = launch_after(k_emit_flagged<2>, grid, dim3(K1_THREADS), 0, st, pdl, Pl); break;
+                case 3: le = launch_after(k_emit_flagged<3>, grid, dim3(K1_THREADS), 0, st, pdl, Pl); break;
+                default: le = launch_after(k_emit_flagged<4>, grid, dim3(K1_THREADS), 0, st, pdl, Pl); break;
                 }
+                if (le != cudaSuccess) return YL_ERR_CUDA_BASE + (int)le;
             }
         } else {
             switch (NW) {

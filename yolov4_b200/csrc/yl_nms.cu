@@ -193,6 +193,17 @@ k_segment_nms_bins(uint4 *__restrict__ cand, const unsigned *__restrict__ seg_co
     __shared__ BinsSmem S;
     const unsigned FULL = 0xFFFFFFFFu;
     const int seg = seg_first + blockIdx.x;
+    pdl_trigger();
+    {
+        // zero the exclusion tables: independent of the input, so a CTA launched early (PDL) does it while the filter
+        // kernel is still draining, and otherwise while the record loads are in flight
+        uint4 *z = reinterpret_cast<uint4 *>(&S.b.tab[0][0][0]);
+        constexpr int NZ = (int)(sizeof(S.b.tab) / sizeof(uint4));
+        for (int i = threadIdx.x; i < NZ; i += SMALL_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (threadIdx.x < SMALL_WARPS) S.qn[threadIdx.x] = 0u;
+        if (threadIdx.x < SMALL_W) S.dirty[threadIdx.x] = 0u;
+    }
+    pdl_wait();                                                 // segment counts and records of the filter kernel
     const unsigned cnt = seg_count[seg];
     if (cnt == 0u) return;                                      // kept_count was zeroed by yl_post_reset
     if (cnt > (unsigned)cap_seg) return;                        // overflow: reported through meta[], caller re-runs
@@ -214,14 +225,6 @@ k_segment_nms_bins(uint4 *__restrict__ cand, const unsigned *__restrict__ seg_co
         ra[u] = make_uint4(0u, 0u, 0u, 0u);
         rb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (e < n) { ra[u] = rec[2 * e]; rb[u] = as_float4(rec[2 * e + 1]); }
-    }
-    {
-        // zero the exclusion tables while the loads are in flight
-        uint4 *z = reinterpret_cast<uint4 *>(&S.b.tab[0][0][0]);
-        constexpr int NZ = (int)(sizeof(S.b.tab) / sizeof(uint4));
-        for (int i = tid; i < NZ; i += SMALL_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
-        if (tid < SMALL_WARPS) S.qn[tid] = 0u;
-        if (tid < SMALL_W) S.dirty[tid] = 0u;
     }
     unsigned key[SMALL_EPT];
     bool valid[SMALL_EPT];
@@ -605,6 +608,8 @@ k_segment_nms_big(uint4 *__restrict__ cand, const unsigned *__restrict__ seg_cou
     __shared__ unsigned sh_supp[2];
     __shared__ int sh_nk;
 
+    pdl_trigger();
+    pdl_wait();                                                 // the queue filled by k_segment_nms_bins
     const unsigned nbig = *big_count;
     for (unsigned it = blockIdx.x; it < nbig; it += gridDim.x) {
         const int seg = (int)big_list[it];
@@ -670,6 +675,7 @@ k_gather_rows(const uint4 *__restrict__ cand, const unsigned *__restrict__ seg_c
               int C, int cap_seg, int B, float *__restrict__ out_rows, long cap_out, int *__restrict__ meta, int seg_first)
 {
     __shared__ unsigned sh_red[3][GATHER_THREADS / 32];
+    pdl_wait();                                                 // kept counts and finished rows of both NMS tiers
     const int seg = seg_first + blockIdx.x;
     const int b = seg / C, c = seg - b * C;
     const int tid = threadIdx.x;
@@ -751,14 +757,15 @@ extern "C" int yl_nms(void *ws, size_t ws_bytes, int B, long M, int C, int cap_s
     unsigned *big_count = (unsigned *)(w + L.off_big_count) + img_first;
     unsigned *big_list = (unsigned *)(w + L.off_big_list) + seg_first;
     cudaStream_t st = (cudaStream_t)stream;
-    k_segment_nms_bins<<<nseg, SMALL_THREADS, 0, st>>>(cand, seg_count, kept_count, C, cap_seg, nms_thre, area_bin_gap(nms_thre),
-                                                      seg_first, big_count, big_list);
-    YL_LAUNCH_CHECK();
+    // each kernel may become resident while its predecessor drains (PDL); it waits before reading the predecessor's output.
+    // The first one follows the emit / dense filter kernel of yl_filter_* on the same stream.
+    const bool pdl = pdl_enabled();
+    YL_CUDA_TRY(launch_after(k_segment_nms_bins, dim3(nseg), dim3(SMALL_THREADS), 0, st, pdl, cand, seg_count, kept_count, C, cap_seg,
+                             nms_thre, area_bin_gap(nms_thre), seg_first, big_count, big_list));
     const int grid_big = nseg < 148 * 2 ? nseg : 148 * 2;
-    k_segment_nms_big<<<grid_big, NMS_THREADS, 0, st>>>(cand, seg_count, kept_count, C, cap_seg, nms_thre, big_count, big_list,
-                                                       kept_scratch);
-    YL_LAUNCH_CHECK();
-    k_gather_rows<<<nseg, GATHER_THREADS, 0, st>>>(cand, seg_count, kept_count, C, cap_seg, B, out_rows, cap_out, meta, seg_first);
-    YL_LAUNCH_CHECK();
+    YL_CUDA_TRY(launch_after(k_segment_nms_big, dim3(grid_big), dim3(NMS_THREADS), 0, st, pdl, cand, (const unsigned *)seg_count, kept_count,
+                             C, cap_seg, nms_thre, (const unsigned *)big_count, (const unsigned *)big_list, kept_scratch));
+    YL_CUDA_TRY(launch_after(k_gather_rows, dim3(nseg), dim3(GATHER_THREADS), 0, st, pdl, (const uint4 *)cand, (const unsigned *)seg_count,
+                             (const unsigned *)kept_count, C, cap_seg, B, out_rows, cap_out, meta, seg_first));
     return YL_OK;
 }
