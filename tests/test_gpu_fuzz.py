@@ -14,3 +14,10 @@ def test_fuzz_parity_fixed_seed():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_parity.py"), "60", "3"], capture_output=True, text=True,
                        timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.gpu
+def test_fuzz_loss_and_build_target_fixed_seed():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_loss.py"), "25", "5"], capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
