@@ -41,16 +41,27 @@ k_decode_dense(const float *__restrict__ raw, int Fw, int F2, int C, float strid
                 const int k = k0 + KR * u;
                 t[u] = (k < nch) ? ldg_stream1(src + (size_t)k * F2) : 0.0f;
             }
+            // two transcendentals per packed instruction stream (spec_sigmoid2 / spec_exp2: same bits as the scalar forms)
+            float sg[8];
+#pragma unroll
+            for (int u = 0; u < 8; u += 2) {
+                if (k0 + KR * u == 2 || k0 + KR * u == 3) {          // tw / th in slot u (first batch only); slot u+1 is a class channel
+                    sg[u] = spec_expf(t[u]);
+                    sg[u + 1] = spec_sigmoidf(t[u + 1]);
+                } else {
+                    spec_sigmoid2(t[u], t[u + 1], sg[u], sg[u + 1]);
+                }
+            }
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const int k = k0 + KR * u;
                 if (k < nch) {
                     float v;
-                    if (k == 0) v = __fmul_rn(__fadd_rn(spec_sigmoidf(t[u]), (float)gx), stride);
-                    else if (k == 1) v = __fmul_rn(__fadd_rn(spec_sigmoidf(t[u]), (float)gy), stride);
-                    else if (k == 2) v = __fmul_rn(__fmul_rn(spec_expf(t[u]), aw), stride);
-                    else if (k == 3) v = __fmul_rn(__fmul_rn(spec_expf(t[u]), ah), stride);
-                    else v = spec_sigmoidf(t[u]);
+                    if (k == 0) v = __fmul_rn(__fadd_rn(sg[u], (float)gx), stride);
+                    else if (k == 1) v = __fmul_rn(__fadd_rn(sg[u], (float)gy), stride);
+                    else if (k == 2) v = __fmul_rn(__fmul_rn(sg[u], aw), stride);
+                    else if (k == 3) v = __fmul_rn(__fmul_rn(sg[u], ah), stride);
+                    else v = sg[u];
                     tile[pl * nchp + k] = v;
                 }
             }
@@ -89,20 +100,29 @@ k_decode_train(const float *__restrict__ raw, int Fw, int F2, int C, long total,
         Vec<VEC> t;
         t.load(raw + idx);
         float o[VEC];
+        if (VEC == 4 && k != 2 && k != 3) {                                   // yololayer.py:105, two values per packed op
+            spec_sigmoid2(t.v[0], t.v[1 % VEC], o[0], o[1 % VEC]);
+            spec_sigmoid2(t.v[2 % VEC], t.v[3 % VEC], o[2 % VEC], o[3 % VEC]);
+        } else {
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) o[v] = (k != 2 && k != 3) ? spec_sigmoidf(t.v[v]) : t.v[v];      // yololayer.py:105
+            for (int v = 0; v < VEC; ++v) o[v] = (k != 2 && k != 3) ? spec_sigmoidf(t.v[v]) : t.v[v];
+        }
         if (VEC == 4) *reinterpret_cast<float4 *>(output_planar + idx) = make_float4(o[0], o[1 % VEC], o[2 % VEC], o[3 % VEC]);
         else output_planar[idx] = o[0];
         if (k < 4) {
             const int a = ba % 3;
-            float pv[VEC];
+            float pv[VEC], ex[VEC];
+            if (k >= 2) {
+                if (VEC == 4) { spec_exp2(t.v[0], t.v[1 % VEC], ex[0], ex[1 % VEC]); spec_exp2(t.v[2 % VEC], t.v[3 % VEC], ex[2 % VEC], ex[3 % VEC]); }
+                else ex[0] = spec_expf(t.v[0]);
+            }
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
                 const int pp = p + v;
                 if (k == 0) pv[v] = __fadd_rn(o[v], (float)(pp % Fw));                   // :126
                 else if (k == 1) pv[v] = __fadd_rn(o[v], (float)(pp / Fw));              // :129
-                else if (k == 2) pv[v] = __fmul_rn(spec_expf(t.v[v]), (a == 0) ? aw0 : ((a == 1) ? aw1 : aw2));   // :132
-                else pv[v] = __fmul_rn(spec_expf(t.v[v]), (a == 0) ? ah0 : ((a == 1) ? ah1 : ah2));               // :134
+                else if (k == 2) pv[v] = __fmul_rn(ex[v], (a == 0) ? aw0 : ((a == 1) ? aw1 : aw2));               // :132
+                else pv[v] = __fmul_rn(ex[v], (a == 0) ? ah0 : ((a == 1) ? ah1 : ah2));                           // :134
             }
             float *dst = pred_planar + ((size_t)ba * 4 + k) * F2 + p;
             if (VEC == 4) *reinterpret_cast<float4 *>(dst) = make_float4(pv[0], pv[1 % VEC], pv[2 % VEC], pv[3 % VEC]);
