@@ -34,37 +34,46 @@ k_decode_dense(const float *__restrict__ raw, int Fw, int F2, int C, float strid
         const int gy = p / Fw, gx = p - gy * Fw;
         const float *src = raw + ((size_t)ba * nch) * F2 + p;
         constexpr int KR = DD_THREADS / DD_TP;                       // channel rows per pass
-        for (int k0 = kr; k0 < nch; k0 += KR * 8) {                  // eight loads in flight per thread, then the math
+        // first batch of eight channels (k = kr, kr+4, ...): slot 0 is one of tx, ty, tw, th; the others are obj / classes
+        {
+            float t[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int k = kr + KR * u;
+                t[u] = (k < nch) ? ldg_stream1(src + (size_t)k * F2) : 0.0f;
+            }
+            float sg[8];
+            if (kr >= 2) { sg[0] = spec_expf(t[0]); sg[1] = spec_sigmoidf(t[1]); }
+            else spec_sigmoid2(t[0], t[1], sg[0], sg[1]);
+#pragma unroll
+            for (int u = 2; u < 8; u += 2) spec_sigmoid2(t[u], t[u + 1], sg[u], sg[u + 1]);
+            float v0;
+            if (kr == 0) v0 = __fmul_rn(__fadd_rn(sg[0], (float)gx), stride);
+            else if (kr == 1) v0 = __fmul_rn(__fadd_rn(sg[0], (float)gy), stride);
+            else if (kr == 2) v0 = __fmul_rn(__fmul_rn(sg[0], aw), stride);
+            else v0 = __fmul_rn(__fmul_rn(sg[0], ah), stride);
+            float *tp = tile + pl * nchp + kr;
+            tp[0] = v0;
+#pragma unroll
+            for (int u = 1; u < 8; ++u)
+                if (kr + KR * u < nch) tp[KR * u] = sg[u];
+        }
+        // the remaining batches are class channels only: two sigmoids per packed instruction stream
+        // (spec_sigmoid2: same bits as the scalar form), no per-channel case analysis
+        for (int k0 = kr + KR * 8; k0 < nch; k0 += KR * 8) {         // eight loads in flight per thread, then the math
             float t[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const int k = k0 + KR * u;
                 t[u] = (k < nch) ? ldg_stream1(src + (size_t)k * F2) : 0.0f;
             }
-            // two transcendentals per packed instruction stream (spec_sigmoid2 / spec_exp2: same bits as the scalar forms)
             float sg[8];
 #pragma unroll
-            for (int u = 0; u < 8; u += 2) {
-                if (k0 + KR * u == 2 || k0 + KR * u == 3) {          // tw / th in slot u (first batch only); slot u+1 is a class channel
-                    sg[u] = spec_expf(t[u]);
-                    sg[u + 1] = spec_sigmoidf(t[u + 1]);
-                } else {
-                    spec_sigmoid2(t[u], t[u + 1], sg[u], sg[u + 1]);
-                }
-            }
+            for (int u = 0; u < 8; u += 2) spec_sigmoid2(t[u], t[u + 1], sg[u], sg[u + 1]);
+            float *tp = tile + pl * nchp + k0;
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int k = k0 + KR * u;
-                if (k < nch) {
-                    float v;
-                    if (k == 0) v = __fmul_rn(__fadd_rn(sg[u], (float)gx), stride);
-                    else if (k == 1) v = __fmul_rn(__fadd_rn(sg[u], (float)gy), stride);
-                    else if (k == 2) v = __fmul_rn(__fmul_rn(sg[u], aw), stride);
-                    else if (k == 3) v = __fmul_rn(__fmul_rn(sg[u], ah), stride);
-                    else v = sg[u];
-                    tile[pl * nchp + k] = v;
-                }
-            }
+            for (int u = 0; u < 8; ++u)
+                if (k0 + KR * u < nch) tp[KR * u] = sg[u];
         }
     }
     __syncthreads();
