@@ -79,6 +79,24 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa(index):
+    """Multi-GPU end-to-end leg: every rank uploads 495 MB per step from pinned host memory, so the rank's pages should
+    live on the NUMA node its GPU hangs off.  Binds the process to the GPU's CPU affinity mask (NVML) before any host
+    buffer is allocated; silently does nothing where NVML or the mask is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n = os.cpu_count() or 1
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, (n + 63) // 64)
+        cpus = [i for i in range(n) if (mask[i // 64] >> (i % 64)) & 1]
+        if cpus and len(cpus) < n:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return None
+
+
 def cpu_baseline(sample_images, threads, seed=0, min_seconds=0.0):
     """Oracle port of the reference CPU path (decode x3 + cat + postprocess) on `sample_images` images of the workload."""
     import torch
@@ -153,6 +171,8 @@ def main():
     from yolov4_b200 import _cabi
     from yolov4_b200.synth import synth_head_outputs
 
+    if world > 1:
+        bind_to_gpu_numa(local_rank)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
