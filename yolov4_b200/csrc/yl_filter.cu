@@ -871,6 +871,14 @@ k_filter_dense(const float *__restrict__ pred, long M, int C, int num_classes, f
             }
         }
     };
+    // per-lane channel roles, the same for every row: slot j holds channel 32 j + lane
+    bool isch[NJ], isfirst[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        const int idx = 32 * j + lane;
+        isch[j] = idx < nch;
+        isfirst[j] = idx >= 5 && idx < 5 + num_classes;
+    }
     long g0 = g_first + wid * KD_GROUPS;
     if (g0 < g_end) load_round(g0);
     while (g0 < g_end) {
@@ -891,10 +899,14 @@ k_filter_dense(const float *__restrict__ pred, long M, int C, int num_classes, f
             const float *st = stage[warp][rr >> 2] + (rr & 3) * nch;
             float e[NJ];
 #pragma unroll
-            for (int j = 0; j < NJ; ++j) {
-                const int idx = 32 * j + lane;
-                e[j] = (idx < nch) ? st[idx] : 0.0f;
-            }
+            for (int j = 0; j < NJ; ++j) e[j] = isch[j] ? st[32 * j + lane] : 0.0f;
+            // ~92 % of the rows end here: with obj >= 0 a row produces something only if one of its first num_classes
+            // classes passes the per-class test (see dense_row); NaN / negative objectness always take the full path
+            const float obj = st[4];
+            bool hit = false;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) hit |= isfirst[j] && (__fmul_rn(e[j], obj) >= thr);
+            if (obj >= 0.0f && !__any_sync(0xFFFFFFFFu, hit)) continue;      // warp-uniform
             dense_row<NJ>(e, nch, C, num_classes, thr, cap_seg, r0 + rr, M, cand, seg_count);
         }
         __syncwarp();                                                         // all lanes have read the stage
