@@ -839,7 +839,7 @@ k_filter_dense(const float *__restrict__ pred, long M, int C, int num_classes, f
                long row_first, long row_end, long rows_total,
                uint4 *__restrict__ cand, unsigned *__restrict__ seg_count)
 {
-    __shared__ __align__(16) float stage[KD_WARPS][KD_GROUPS][4 * 32 * NJ];
+    __shared__ __align__(16) float stage[KD_WARPS][KD_GROUPS * 4 * 32 * NJ];   // the round's 8 rows back to back: row rr at rr*nch
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long wid = ((long)blockIdx.x * KD_THREADS + threadIdx.x) >> 5;
     const long nwarps = ((long)gridDim.x * KD_THREADS) >> 5;
@@ -849,6 +849,16 @@ k_filter_dense(const float *__restrict__ pred, long M, int C, int num_classes, f
     const float4 *p4 = reinterpret_cast<const float4 *>(pred);
     float4 v[KD_GROUPS][NJ];
     auto load_round = [&](long g0) {
+        if (g0 + KD_GROUPS <= g_end && (g0 + KD_GROUPS) * nch <= total4) {
+            // the whole round lies inside the tensor (every round but the last few): no per-load bounds arithmetic
+            const float4 *src = p4 + g0 * nch + lane;
+#pragma unroll
+            for (int q = 0; q < KD_GROUPS; ++q)
+#pragma unroll
+                for (int j = 0; j < NJ; ++j)
+                    if (32 * j + lane < nch) v[q][j] = ldg_stream4(reinterpret_cast<const float *>(src + q * nch + 32 * j));
+            return;
+        }
 #pragma unroll
         for (int q = 0; q < KD_GROUPS; ++q) {
             const long base4 = (g0 + q) * nch;                                // group g = float4s [g*nch, (g+1)*nch)
@@ -871,13 +881,13 @@ k_filter_dense(const float *__restrict__ pred, long M, int C, int num_classes, f
             }
         }
     };
-    // per-lane channel roles, the same for every row: slot j holds channel 32 j + lane
-    bool isch[NJ], isfirst[NJ];
+    // per-lane threshold of the fast row test: slot j holds channel 32 j + lane; only the first num_classes class channels
+    // can make a row interesting, every other slot gets +inf (never passes; what it reads is in-bounds scratch)
+    float thr_j[NJ];
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
         const int idx = 32 * j + lane;
-        isch[j] = idx < nch;
-        isfirst[j] = idx >= 5 && idx < 5 + num_classes;
+        thr_j[j] = (idx >= 5 && idx < 5 + num_classes) ? thr : kInf;
     }
     long g0 = g_first + wid * KD_GROUPS;
     if (g0 < g_end) load_round(g0);
@@ -887,25 +897,25 @@ k_filter_dense(const float *__restrict__ pred, long M, int C, int num_classes, f
 #pragma unroll
             for (int j = 0; j < NJ; ++j) {
                 const int i = 32 * j + lane;
-                if (i < nch) reinterpret_cast<float4 *>(stage[warp][q])[i] = v[q][j];
+                if (i < nch) reinterpret_cast<float4 *>(stage[warp])[q * nch + i] = v[q][j];
             }
         __syncwarp();
         const long gn = g0 + nwarps * KD_GROUPS;
         if (gn < g_end) load_round(gn);                                       // the next round is in flight while this one is walked
         const long r0 = g0 * 4;
         const int rr_lo = (int)max(0L, row_first - r0), rr_hi = (int)min((long)(4 * KD_GROUPS), row_end - r0);
+        const float *st = stage[warp] + rr_lo * nch + lane;
 #pragma unroll 1
-        for (int rr = rr_lo; rr < rr_hi; ++rr) {                              // rows of this round inside [row_first, row_end)
-            const float *st = stage[warp][rr >> 2] + (rr & 3) * nch;
-            float e[NJ];
-#pragma unroll
-            for (int j = 0; j < NJ; ++j) e[j] = isch[j] ? st[32 * j + lane] : 0.0f;
+        for (int rr = rr_lo; rr < rr_hi; ++rr, st += nch) {                   // rows of this round inside [row_first, row_end)
             // ~92 % of the rows end here: with obj >= 0 a row produces something only if one of its first num_classes
             // classes passes the per-class test (see dense_row); NaN / negative objectness always take the full path
-            const float obj = st[4];
+            float e[NJ];
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) e[j] = st[32 * j];
+            const float obj = st[4 - lane];
             bool hit = false;
 #pragma unroll
-            for (int j = 0; j < NJ; ++j) hit |= isfirst[j] && (__fmul_rn(e[j], obj) >= thr);
+            for (int j = 0; j < NJ; ++j) hit |= (__fmul_rn(e[j], obj) >= thr_j[j]);
             if (obj >= 0.0f && !__any_sync(0xFFFFFFFFu, hit)) continue;      // warp-uniform
             dense_row<NJ>(e, nch, C, num_classes, thr, cap_seg, r0 + rr, M, cand, seg_count);
         }
