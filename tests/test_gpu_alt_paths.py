@@ -10,9 +10,8 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-@pytest.mark.parametrize("env", [{}, {"YL_FILTER": "fused"}, {"YL_FILTER": "fused", "YL_NO_TMA": "1"}, {"YL_FILTER": "cm"},
-                          {"YL_FILTER": "split"}],
-                         ids=["default", "fused-tma", "fused-ldg", "class-major", "split"])
+@pytest.mark.parametrize("env", [{}, {"YL_FILTER": "fused"}, {"YL_FILTER": "fused", "YL_NO_TMA": "1"}],
+                         ids=["default", "fused-tma", "fused-ldg"])
 def test_kernel_forms_match_oracle(env):
     e = dict(os.environ)
     e.update(env)

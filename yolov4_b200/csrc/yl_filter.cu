@@ -38,6 +38,32 @@ __device__ __forceinline__ void flag_or(unsigned &bits, float t, float lth, unsi
     asm("{\n\t.reg .pred p;\n\tsetp.lt.f32 p, %1, %2;\n\t@!p or.b32 %0, %0, %3;\n\t}" : "+r"(bits) : "f"(t), "f"(lth), "r"(bit));
 }
 
+// One scale of the head as the kernel sees it.
+struct RawLayer {
+    const float *raw;      // [B, 3, 5+C, F, F]
+    int Fw, F2;
+    int row_off;           // rows of the lower scales in the concatenated [M] axis (yolov4.py:324)
+    int tiles;             // CTAs along x for this scale
+    int vec;               // 4 = 128-bit loads, 1 = scalar loads (planes not 16-byte aligned, e.g. 19x19)
+    int tma;               // streamed with TMA by k_filter_raw_tma (else register-staged loads)
+    int tile_boxes;        // boxes per warp tile in k_filter_raw_tma (128 TMA, 32 scalar)
+    float stride;
+    float aw[3], ah[3];    // masked anchors in grid units (yololayer.py:73-76)
+};
+struct RawParams {
+    RawLayer layer[3];
+    int n_layers, C, cap_seg, img_first;
+    int sparse;            // high thresholds: look at the objectness plane first and skip the class planes of dead vectors
+    long M;
+    float thr;
+    uint4 *cand;
+    unsigned *seg_count;
+    float *objtab;         // split filter: sigmoid(objectness) of every box, flag kernel -> emit kernel
+    unsigned *flags;       // split filter: [NW][B*M4] flag words (see PostLayout)
+    long M4;               // row pitch of flags / objtab in split mode (M rounded up to 4)
+    long BM4;              // B * M4
+};
+
 constexpr int K1_WARPS = K1_THREADS / 32;
 constexpr int K1_QCAP = 256;           // flagged (box,class) pairs a warp resolves per batch (a box has at most 128)
 
@@ -49,6 +75,17 @@ struct EmitWarp {
     unsigned flg[4];                   // per box slot: belongs to the batch being resolved (speculative box fetch)
     float4 box[128];                   // decoded corners of the box slots that have a surviving pair
 };
+
+__device__ __forceinline__ float4 decode_box_v(float tx, float ty, float tw, float th, int Fw, int p, float aw, float ah, float stride)
+{
+    const int gy = p / Fw, gx = p - gy * Fw;
+    const float bx = __fmul_rn(__fadd_rn(spec_sigmoidf(tx), (float)gx), stride);
+    const float by = __fmul_rn(__fadd_rn(spec_sigmoidf(ty), (float)gy), stride);
+    const float bw = __fmul_rn(__fmul_rn(spec_expf(tw), aw), stride);
+    const float bh = __fmul_rn(__fmul_rn(spec_expf(th), ah), stride);
+    const float hw = __fmul_rn(bw, 0.5f), hh = __fmul_rn(bh, 0.5f);
+    return make_float4(__fsub_rn(bx, hw), __fsub_rn(by, hh), __fadd_rn(bx, hw), __fadd_rn(by, hh));
+}
 
 // Decode one box (yololayer.py:150-162) and convert to corners (utils.py:117-126).
 __device__ __forceinline__ float4 decode_box(const float *bp, int F2, int Fw, int p, float aw, float ah, float stride)
@@ -421,153 +458,6 @@ k_flag_raw(const __grid_constant__ RawParams P)
     while (l < P.n_layers - 1 && tile >= P.layer[l].tiles) { tile -= P.layer[l].tiles; ++l; }
     if (P.layer[l].vec == 4) flag_tile<4, NW>(P, P.layer[l], tile, ba);
     else flag_tile<1, NW>(P, P.layer[l], tile, ba);
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// Class-major form (YL_FILTER=cm): the streaming kernel writes, per (image, class), a bitmap over the boxes whose class
-// logit reaches the conservative bound -- a warp ballot per (class, vector element) instead of a per-thread flag word
-// -- and there is no emit kernel: the CTA of k_segment_nms_bins that owns the (image, class) segment scans its 3 KB
-// bitmap row, fetches the flagged logits / box planes itself and builds its records directly in shared memory
-// (yl_nms.cu, cm_front_end).  No candidate records, slot atomics or segment counters cross global memory.
-// Bit layout of a row: scale l starts at word layer[l].cb_base; word ((a*tiles + tile)*4 + warp)*VEC + v, bit `lane`
-// is box p = ((tile*128 + warp*32 + lane)*VEC + v of anchor a (the ballot order of the warp that streams those boxes).
-// A box with a NaN class logit is dropped as a whole by the reference (torch.max, utils.py:139-148): its
-// sigmoid(objectness) entry is replaced by NaN, which fails every exact test downstream.
-// ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float max_nan(float a, float b)
-{
-    float d;
-    asm("max.NaN.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
-    return d;
-}
-
-template <int VEC>
-__device__ __forceinline__ void cm_class(const Vec<VEC> &t, const float (&lth)[VEC], float (&nanacc)[VEC], unsigned *dst, int lane)
-{
-    unsigned w[VEC];
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) {
-        w[v] = __ballot_sync(0xFFFFFFFFu, !(t.v[v] < lth[v]));
-        nanacc[v] = max_nan(nanacc[v], t.v[v]);
-    }
-    if (lane == 0) {
-        if (VEC == 4) stg_keep4(dst, make_uint4(w[0], w[1 % VEC], w[2 % VEC], w[3 % VEC]));
-        else stg_keep1(dst, w[0]);
-    }
-}
-
-template <int VEC, int NW>
-__device__ __forceinline__ void flag_cm_tile(const RawParams &P, const RawLayer &Ly, int tile, int ba)
-{
-    const unsigned FULL = 0xFFFFFFFFu;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int C = P.C, F2 = Ly.F2;
-    const float thr = P.thr;
-    const int p0 = (tile * K1_THREADS + threadIdx.x) * VEC;
-    const bool inb = p0 < F2;                                        // F2 % VEC == 0: a vector is all in or all out
-    const int b = ba / 3, a = ba - 3 * b;
-    const float *base = Ly.raw + ((size_t)ba * (5 + C)) * F2 + (inb ? p0 : 0);
-    const float *cp = base + 5 * (size_t)F2;
-    const size_t pitch = (size_t)P.cb_pitch;
-    unsigned *dst = P.cbits + (size_t)b * C * pitch + Ly.cb_base + ((a * Ly.tiles + tile) * K1_WARPS + warp) * VEC;
-    Vec<VEC> tob, t0[8];
-    const int kn0 = min(8, C);
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) tob.v[v] = 0.0f;
-#pragma unroll
-    for (int u = 0; u < 8; ++u)
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) t0[u].v[v] = 0.0f;
-    float obj[VEC], lth[VEC], nanacc[VEC];
-    bool alive = false;
-    if (P.sparse) {
-        if (inb) tob.load(base + 4 * (size_t)F2);
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-            obj[v] = inb ? spec_sigmoidf(tob.v[v]) : 0.0f;
-            lth[v] = inb ? class_logit_bound(obj[v], thr) : kInf;
-            alive |= (lth[v] != kInf);
-        }
-        if (alive) {
-#pragma unroll
-            for (int u = 0; u < 8; ++u)
-                if (u < kn0) t0[u].load(cp + (size_t)u * F2);
-        }
-    } else {
-        if (inb) {
-            tob.load(base + 4 * (size_t)F2);
-#pragma unroll
-            for (int u = 0; u < 8; ++u)
-                if (u < kn0) t0[u].load(cp + (size_t)u * F2);
-        }
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-            obj[v] = inb ? spec_sigmoidf(tob.v[v]) : 0.0f;
-            lth[v] = inb ? class_logit_bound(obj[v], thr) : kInf;
-            alive |= (lth[v] != kInf);
-        }
-    }
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) nanacc[v] = 0.0f;
-    if (__any_sync(FULL, alive)) {
-#pragma unroll
-        for (int u = 0; u < 8; ++u)
-            if (u < kn0) cm_class<VEC>(t0[u], lth, nanacc, dst + (size_t)u * pitch, lane);
-#pragma unroll
-        for (int w = 0; w < NW; ++w) {
-            const int kn = min(32, C - 32 * w);
-#pragma unroll
-            for (int kk = (w == 0 ? 8 : 0); kk < 32; kk += 8) {
-                if (kk < kn) {
-                    Vec<VEC> t[8];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-#pragma unroll
-                        for (int v = 0; v < VEC; ++v) t[u].v[v] = 0.0f;
-                        if (kk + u < kn && alive) t[u].load(cp + (size_t)(32 * w + kk + u) * F2);
-                    }
-#pragma unroll
-                    for (int u = 0; u < 8; ++u)
-                        if (kk + u < kn) cm_class<VEC>(t[u], lth, nanacc, dst + (size_t)(32 * w + kk + u) * pitch, lane);
-                }
-            }
-        }
-    } else {
-        // nothing alive in these 32*VEC boxes: the rows still have to read as zero
-        for (int c = lane; c < C; c += 32) {
-            if (VEC == 4) stg_keep4(dst + (size_t)c * pitch, make_uint4(0u, 0u, 0u, 0u));
-            else stg_keep1(dst + (size_t)c * pitch, 0u);
-        }
-    }
-    if (inb) {
-#pragma unroll
-        for (int v = 0; v < VEC; ++v)
-            if (nanacc[v] != nanacc[v]) obj[v] = nanacc[v];
-        const size_t r = (size_t)b * P.M4 + (Ly.row_off + a * F2 + p0);
-        if (VEC == 4) stg_keep4(P.objtab + r, make_uint4(__float_as_uint(obj[0]), __float_as_uint(obj[1 % VEC]),
-                                                         __float_as_uint(obj[2 % VEC]), __float_as_uint(obj[3 % VEC])));
-        else stg_keep1(P.objtab + r, __float_as_uint(obj[0]));
-    }
-}
-
-template <int NW>
-__global__ void __launch_bounds__(K1_THREADS, YL_FLAG_MINB)
-k_flag_cm(const __grid_constant__ RawParams P, CmHeader *__restrict__ hdr)
-{
-    pdl_trigger();
-    if (blockIdx.x == 0 && blockIdx.y == 0) {
-        // the NMS kernel reads the head description from the workspace: its C-ABI entry point takes no raw pointers
-        const unsigned *src = reinterpret_cast<const unsigned *>(&P);
-        unsigned *d = reinterpret_cast<unsigned *>(&hdr->P);
-        for (int i = threadIdx.x; i < (int)(sizeof(RawParams) / sizeof(unsigned)); i += K1_THREADS) d[i] = src[i];
-        if (threadIdx.x == 0) hdr->mode = 1u;
-    }
-    const int ba = P.img_first * 3 + blockIdx.y;
-    int tile = blockIdx.x;
-    int l = 0;
-    while (l < P.n_layers - 1 && tile >= P.layer[l].tiles) { tile -= P.layer[l].tiles; ++l; }
-    if (P.layer[l].vec == 4) flag_cm_tile<4, NW>(P, P.layer[l], tile, ba);
-    else flag_cm_tile<1, NW>(P, P.layer[l], tile, ba);
 }
 
 template <int VEC, int NW>
@@ -1069,8 +959,6 @@ static const bool g_use_tma = !(getenv("YL_NO_TMA") && getenv("YL_NO_TMA")[0] ==
 // YL_FILTER selects the front-end form: "split" (default: lean streaming flag kernel + emit kernel),
 // "fused" (one kernel streams and emits: the TMA pipeline where planes are 16-byte aligned, register-staged otherwise).
 static const bool g_split = !(getenv("YL_FILTER") && strcmp(getenv("YL_FILTER"), "fused") == 0);
-// "cm": class-major flag bitmaps, no emit kernel (the NMS kernel builds its own records); launched like the split form.
-static const bool g_cm = getenv("YL_FILTER") && strcmp(getenv("YL_FILTER"), "cm") == 0;
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda).
 static int encode_plane_map(CUtensorMap *map, const float *raw, int F2, long rows)
 {
@@ -1136,13 +1024,12 @@ static int filter_raw_impl(const float *const *raw, const int *F, int n_layers, 
     base.sparse = conf_thre >= 0.02f ? 1 : 0;     // sigmoid(obj) >= 0.02 is rare for background cells (obj logit >= -3.9)
     base.cand = cand; base.seg_count = seg_count; base.objtab = objtab; base.n_layers = 0;
     base.flags = (unsigned *)(w + L.off_flags); base.M4 = L.M4; base.BM4 = (long)B * L.M4;
-    base.cbits = (unsigned *)(w + L.off_cbits); base.cb_pitch = L.cb_pitch; base.cb_words = 0;
     RawParams Pt = base, Pl = base;                 // Pt: persistent TMA kernel (TMA scales first, scalar scales last); Pl: LDG kernel
     RawLayer lay[3];
     int row_off = 0, tiles_tma = 0, tiles_ldg = 0, n_tma = 0;
     for (int l = 0; l < n_layers; ++l) {
         RawLayer &Ly = lay[l];
-        Ly.raw = raw[l]; Ly.Fw = F[l]; Ly.F2 = F[l] * F[l]; Ly.row_off = row_off; Ly.cb_base = 0;
+        Ly.raw = raw[l]; Ly.Fw = F[l]; Ly.F2 = F[l] * F[l]; Ly.row_off = row_off;
         Ly.stride = (float)(8 << l);                                        // yololayer.py:54
         for (int a = 0; a < 3; ++a) {                                       // yololayer.py:73-76 (doubles, then fp32)
             const int q = anchor_mask[3 * l + a];
@@ -1156,7 +1043,7 @@ static int filter_raw_impl(const float *const *raw, const int *F, int n_layers, 
         n_tma += Ly.tma;
         row_off += 3 * Ly.F2;
     }
-    if (g_split || g_cm) n_tma = 0;
+    if (g_split) n_tma = 0;
     for (int pass = 0; pass < 2; ++pass)
         for (int l = 0; l < n_layers; ++l) {
             RawLayer Ly = lay[l];
@@ -1170,8 +1057,6 @@ static int filter_raw_impl(const float *const *raw, const int *F, int n_layers, 
                 Ly.tma = 0;
                 Ly.tile_boxes = K1_THREADS * Ly.vec;
                 Ly.tiles = (Ly.F2 / Ly.vec + K1_THREADS - 1) / K1_THREADS;
-                Ly.cb_base = Pl.cb_words;
-                Pl.cb_words += 3 * Ly.tiles * K1_WARPS * Ly.vec;
                 tiles_ldg += Ly.tiles;
                 Pl.layer[Pl.n_layers++] = Ly;
             }
@@ -1211,19 +1096,7 @@ static int filter_raw_impl(const float *const *raw, const int *F, int n_layers, 
     }
     if (Pl.n_layers > 0) {
         dim3 grid(tiles_ldg, img_count * 3);
-        if (g_cm) {
-            if (Pl.cb_words > L.cb_pitch) return YL_ERR_WORKSPACE;
-            if (stages & 1) {
-                CmHeader *hdr = (CmHeader *)(w + L.off_cm);
-                switch (NW) {
-                case 1: k_flag_cm<1><<<grid, K1_THREADS, 0, st>>>(Pl, hdr); break;
-                case 2: k_flag_cm<2><<<grid, K1_THREADS, 0, st>>>(Pl, hdr); break;
-                case 3: k_flag_cm<3><<<grid, K1_THREADS, 0, st>>>(Pl, hdr); break;
-                default: k_flag_cm<4><<<grid, K1_THREADS, 0, st>>>(Pl, hdr); break;
-                }
-                YL_LAUNCH_CHECK();
-            }
-        } else if (g_split) {
+        if (g_split) {
             if (stages & 1) {
                 switch (NW) {
                 case 1: k_flag_raw<1><<<grid, K1_THREADS, 0, st>>>(Pl); break;

@@ -185,188 +185,14 @@ __device__ __forceinline__ int coord_bin(float v, float lo, float scale)
     return min(max(q, 0), NBIN - 1);
 }
 
-// ---- class-major front end (YL_FILTER=cm) ---------------------------------------------------------------------
-// The segment's candidates are not in `cand`: k_flag_cm left a bitmap of the boxes whose class logit reaches the
-// conservative bound.  The CTA turns the bitmap into a list of flagged boxes, fetches objectness (sigmoid, from the
-// flag kernel), the class logit and the four box logits of each, applies the exact test of the emit kernel
-// (fl(obj * sigmoid(t)) >= conf, yl_filter.cu emit_batch), decodes the box and compacts the survivors into the
-// register layout the rest of k_segment_nms_bins expects (record e in thread e % THREADS).
-struct CmRec {
-    uint4 a;       // {score bits, box row, cls_conf bits, obj_conf bits}
-    float4 b;      // corners
-    bool pass;
-};
-
-__device__ __forceinline__ CmRec cm_build(const RawParams &P, unsigned code, int b, int c)
-{
-    const int wd = (int)(code >> 5), bit = (int)(code & 31u);
-    int l = 0;
-    while (l < P.n_layers - 1 && wd >= P.layer[l + 1].cb_base) ++l;
-    const RawLayer &Ly = P.layer[l];
-    const int vec = Ly.vec, F2 = Ly.F2;
-    const int rel = wd - Ly.cb_base;                            // ((a*tiles + tile)*4 + warp)*vec + v
-    const int t2 = rel / vec, v = rel - t2 * vec;
-    const int wq = t2 & 3, t3 = t2 >> 2;
-    const int a = t3 / Ly.tiles, tile = t3 - a * Ly.tiles;
-    const int p = ((tile * 4 + wq) * 32 + bit) * vec + v;
-    const int row = Ly.row_off + a * F2 + p;
-    const float *bp = Ly.raw + ((size_t)(b * 3 + a) * (5 + P.C)) * F2 + p;
-    const float so = P.objtab[(size_t)b * P.M4 + row];
-    const float t = bp[(size_t)(5 + c) * F2];
-    const float tx = bp[0], ty = bp[(size_t)F2], tw = bp[2 * (size_t)F2], th = bp[3 * (size_t)F2];
-    CmRec R;
-    const float cls = spec_sigmoidf(t);
-    const float prod = __fmul_rn(so, cls);
-    R.pass = prod >= P.thr;                                     // NaN objectness (also the NaN-row mark) and NaN logits fail
-    const float sc = __fadd_rn(prod, 0.0f);                     // +0 canonicalises -0
-    R.a = make_uint4(__float_as_uint(sc), (unsigned)row, __float_as_uint(cls), __float_as_uint(so));
-    R.b = decode_box_v(tx, ty, tw, th, Ly.Fw, p, Ly.aw[a], Ly.ah[a], Ly.stride);
-    return R;
-}
-
-// Exclusive prefix of `cnt` over the CTA (thread-major order) and the CTA total; scratch = SMALL_WARPS words.
-__device__ __forceinline__ int cm_scan(int cnt, unsigned *scratch, int &total)
-{
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int incl = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-        if (lane >= o) incl += t;
-    }
-    if (lane == 31) scratch[warp] = (unsigned)incl;
-    __syncthreads();
-    int base = 0;
-    total = 0;
-#pragma unroll
-    for (int wq = 0; wq < SMALL_WARPS; ++wq) {
-        const int t = (int)scratch[wq];
-        if (wq < warp) base += t;
-        total += t;
-    }
-    return base + incl - cnt;
-}
-
-// Slow path: rebuild the segment's records from the bitmap and append them to `cand` through slot atomics, as the emit
-// kernel would have written them, then hand the segment to the big tier (more flagged boxes than the small tier holds,
-// thr <= 0, or a dense overlap graph found later).  seg_count[seg] must be 0 on entry.
-__device__ __noinline__ void cm_spill(const RawParams &P, const uint4 *__restrict__ bm4, int W4, int seg, int b, int c, int cap_seg,
-                                      uint4 *__restrict__ cand, unsigned *__restrict__ seg_count,
-                                      unsigned *__restrict__ big_count, unsigned *__restrict__ big_list)
-{
-    const int tid = threadIdx.x;
-    for (int i = tid; i < W4; i += SMALL_THREADS) {
-        const uint4 w = bm4[i];
-        const unsigned ww[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            unsigned m = ww[j];
-            while (m) {
-                const int k = __ffs(m) - 1;
-                m &= m - 1u;
-                const CmRec R = cm_build(P, (unsigned)(((4 * i + j) << 5) | k), b, c);
-                if (R.pass) {
-                    const unsigned slot = atomicAdd(&seg_count[seg], 1u);
-                    if (slot < (unsigned)cap_seg) {
-                        uint4 *r = cand + ((size_t)seg * cap_seg + slot) * 2;
-                        r[0] = R.a;
-                        r[1] = make_uint4(__float_as_uint(R.b.x), __float_as_uint(R.b.y), __float_as_uint(R.b.z), __float_as_uint(R.b.w));
-                    }
-                }
-            }
-        }
-    }
-    __syncthreads();
-    if (tid == 0) {
-        const unsigned total = atomicAdd(&seg_count[seg], 0u);
-        if (total != 0u && total <= (unsigned)cap_seg) big_list[atomicAdd(big_count, 1u)] = (unsigned)seg;
-    }
-}
-
-// Returns the number of records now in (ra, rb) -- 0 when the segment is empty, was passed on to the big tier or
-// overflows cap_seg (the caller returns).  seg_count[seg] is set to the exact candidate count in every case.
-__device__ __forceinline__ int cm_front_end(const CmHeader *__restrict__ H, BinsSmem &S, int seg, int C, int cap_seg, float nms_thr,
-                                            uint4 *__restrict__ cand, unsigned *__restrict__ seg_count,
-                                            unsigned *__restrict__ big_count, unsigned *__restrict__ big_list,
-                                            uint4 (&ra)[SMALL_EPT], float4 (&rb)[SMALL_EPT])
-{
-    const RawParams &P = H->P;
-    const int tid = threadIdx.x;
-    const int b = seg / C, c = seg - b * C;
-    const int W4 = P.cb_words >> 2;
-    const uint4 *bm4 = reinterpret_cast<const uint4 *>(P.cbits + (size_t)seg * P.cb_pitch);
-    int cnt = 0;
-    for (int i = tid; i < W4; i += SMALL_THREADS) {
-        const uint4 w = bm4[i];
-        cnt += __popc(w.x) + __popc(w.y) + __popc(w.z) + __popc(w.w);
-    }
-    int nf;
-    int pos = cm_scan(cnt, S.keptw, nf);
-    if (nf == 0) return 0;                                      // seg_count / kept_count were zeroed by yl_post_reset
-    if (nf > SMALL_R || !(nms_thr > 0.0f)) {
-        cm_spill(P, bm4, W4, seg, b, c, cap_seg, cand, seg_count, big_count, big_list);
-        return 0;
-    }
-    // list of flagged boxes (word << 5 | bit), thread-major
-    for (int i = tid; i < W4; i += SMALL_THREADS) {
-        const uint4 w = bm4[i];
-        const unsigned ww[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            unsigned m = ww[j];
-            while (m) {
-                const int k = __ffs(m) - 1;
-                m &= m - 1u;
-                S.bins[pos++] = (unsigned)(((4 * i + j) << 5) | k);
-            }
-        }
-    }
-    __syncthreads();
-    CmRec R[SMALL_EPT];
-    int pc = 0;
-#pragma unroll
-    for (int u = 0; u < SMALL_EPT; ++u) {
-        const int e = tid + u * SMALL_THREADS;                  // any order will do: the rank sort orders by the unique key
-        R[u].pass = false;
-        if (e < nf) R[u] = cm_build(P, S.bins[e], b, c);
-        pc += R[u].pass ? 1 : 0;
-    }
-    int n;
-    int q = cm_scan(pc, S.pref, n);
-    if (tid == 0) seg_count[seg] = (unsigned)n;
-    if (n == 0 || n > cap_seg) return 0;                        // overflow: reported through meta[], the caller re-runs
-#pragma unroll
-    for (int u = 0; u < SMALL_EPT; ++u)
-        if (R[u].pass) {
-            S.box[q] = R[u].b;
-            S.co[q] = make_uint2(R[u].a.z, R[u].a.w);
-            S.a.s.k64[q] = ((unsigned long long)R[u].a.x << 32) | R[u].a.y;
-            ++q;
-        }
-    __syncthreads();
-#pragma unroll
-    for (int u = 0; u < SMALL_EPT; ++u) {
-        const int e = tid + u * SMALL_THREADS;
-        ra[u] = make_uint4(0u, 0u, 0u, 0u);
-        rb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (e < n) {
-            const unsigned long long k = S.a.s.k64[e];
-            const uint2 co = S.co[e];
-            ra[u] = make_uint4((unsigned)(k >> 32), (unsigned)k, co.x, co.y);
-            rb[u] = S.box[e];
-        }
-    }
-    __syncthreads();                                            // the staging arrays are free again
-    return n;
-}
-
 __global__ void __launch_bounds__(SMALL_THREADS, YL_NMS_MINB)
-k_segment_nms_bins(uint4 *__restrict__ cand, unsigned *__restrict__ seg_count, unsigned *__restrict__ kept_count,
+k_segment_nms_bins(uint4 *__restrict__ cand, const unsigned *__restrict__ seg_count, unsigned *__restrict__ kept_count,
                    int C, int cap_seg, float thr, int area_k, int seg_first,
-                   unsigned *__restrict__ big_count, unsigned *__restrict__ big_list, const CmHeader *__restrict__ cmh)
+                   unsigned *__restrict__ big_count, unsigned *__restrict__ big_list)
 {
     __shared__ BinsSmem S;
     const unsigned FULL = 0xFFFFFFFFu;
+    const int seg = seg_first + blockIdx.x;
     pdl_trigger();
     {
         // zero the exclusion tables: independent of the input, so a CTA launched early (PDL) does it while the filter
@@ -377,37 +203,29 @@ k_segment_nms_bins(uint4 *__restrict__ cand, unsigned *__restrict__ seg_count, u
         if (threadIdx.x < SMALL_WARPS) S.qn[threadIdx.x] = 0u;
         if (threadIdx.x < SMALL_W) S.dirty[threadIdx.x] = 0u;
     }
-    pdl_wait();                                                 // segment counts and records (or bitmaps) of the filter kernel
+    pdl_wait();                                                 // segment counts and records of the filter kernel
+    const unsigned cnt = seg_count[seg];
+    if (cnt == 0u) return;                                      // kept_count was zeroed by yl_post_reset
+    if (cnt > (unsigned)cap_seg) return;                        // overflow: reported through meta[], caller re-runs
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool cm = cmh->mode != 0u;
-    // class-major form: reverse order of k_flag_cm, whose last images are still in L2 when this kernel starts
-    const int seg = seg_first + (cm ? (int)gridDim.x - 1 - (int)blockIdx.x : (int)blockIdx.x);
+    if (cnt > (unsigned)SMALL_R || !(thr > 0.0f)) {
+        if (tid == 0) big_list[atomicAdd(big_count, 1u)] = (unsigned)seg;
+        return;
+    }
+    const int n = (int)cnt;
+    const int nw = (n + 31) >> 5, nwp = (nw + 1) >> 1;
     uint4 *rec = cand + (size_t)seg * cap_seg * 2;
+
+    // ---- 1. records -> registers; score keys -> shared memory; coordinate range of the segment ----
     uint4 ra[SMALL_EPT];
     float4 rb[SMALL_EPT];
-    int n;
-    if (cm) {
-        n = cm_front_end(cmh, S, seg, C, cap_seg, thr, cand, seg_count, big_count, big_list, ra, rb);
-        if (n == 0) return;
-    } else {
-        const unsigned cnt = seg_count[seg];
-        if (cnt == 0u) return;                                  // kept_count was zeroed by yl_post_reset
-        if (cnt > (unsigned)cap_seg) return;                    // overflow: reported through meta[], caller re-runs
-        if (cnt > (unsigned)SMALL_R || !(thr > 0.0f)) {
-            if (tid == 0) big_list[atomicAdd(big_count, 1u)] = (unsigned)seg;
-            return;
-        }
-        n = (int)cnt;
-        // ---- 1. records -> registers; score keys -> shared memory; coordinate range of the segment ----
 #pragma unroll
-        for (int u = 0; u < SMALL_EPT; ++u) {
-            const int e = tid + u * SMALL_THREADS;
-            ra[u] = make_uint4(0u, 0u, 0u, 0u);
-            rb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (e < n) { ra[u] = rec[2 * e]; rb[u] = as_float4(rec[2 * e + 1]); }
-        }
+    for (int u = 0; u < SMALL_EPT; ++u) {
+        const int e = tid + u * SMALL_THREADS;
+        ra[u] = make_uint4(0u, 0u, 0u, 0u);
+        rb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e < n) { ra[u] = rec[2 * e]; rb[u] = as_float4(rec[2 * e + 1]); }
     }
-    const int nw = (n + 31) >> 5, nwp = (nw + 1) >> 1;
     unsigned key[SMALL_EPT];
     bool valid[SMALL_EPT];
     float lo = kInf, hi = -kInf;
@@ -571,15 +389,6 @@ k_segment_nms_bins(uint4 *__restrict__ cand, unsigned *__restrict__ seg_count, u
     }
     if (__syncthreads_or(overflow)) {
         // dense overlap graph: more candidate pairs than the queue holds -- the chunked big tier takes the segment
-        if (cm) {
-            // its records exist only in this CTA: rebuild them into `cand`
-            const RawParams &P = cmh->P;
-            if (tid == 0) seg_count[seg] = 0u;
-            __syncthreads();
-            cm_spill(P, reinterpret_cast<const uint4 *>(P.cbits + (size_t)seg * P.cb_pitch), P.cb_words >> 2, seg, seg / C, seg % C,
-                     cap_seg, cand, seg_count, big_count, big_list);
-            return;
-        }
         if (tid == 0) big_list[atomicAdd(big_count, 1u)] = (unsigned)seg;
         return;
     }
@@ -952,8 +761,7 @@ extern "C" int yl_nms(void *ws, size_t ws_bytes, int B, long M, int C, int cap_s
     // The first one follows the emit / dense filter kernel of yl_filter_* on the same stream.
     const bool pdl = pdl_enabled();
     YL_CUDA_TRY(launch_after(k_segment_nms_bins, dim3(nseg), dim3(SMALL_THREADS), 0, st, pdl, cand, seg_count, kept_count, C, cap_seg,
-                             nms_thre, area_bin_gap(nms_thre), seg_first, big_count, big_list,
-                             (const CmHeader *)(w + L.off_cm)));
+                             nms_thre, area_bin_gap(nms_thre), seg_first, big_count, big_list));
     const int grid_big = nseg < 148 * 2 ? nseg : 148 * 2;
     YL_CUDA_TRY(launch_after(k_segment_nms_big, dim3(grid_big), dim3(NMS_THREADS), 0, st, pdl, cand, (const unsigned *)seg_count, kept_count,
                              C, cap_seg, nms_thre, (const unsigned *)big_count, (const unsigned *)big_list, kept_scratch));
