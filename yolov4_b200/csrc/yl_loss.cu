@@ -141,15 +141,16 @@ k_loss_obj(const float *__restrict__ raw, const float *__restrict__ labels, int 
     __shared__ __align__(16) float tc[TG_MAXK][4];
     __shared__ float tcls[TG_MAXK];
     __shared__ float tarea[TG_MAXK];
-    __shared__ unsigned char tsimple[TG_MAXK];
-    __shared__ int sh_n;
+    __shared__ unsigned char tns[TG_MAXK];
+    __shared__ float tkey[TG_MAXK];
+    __shared__ int sh_n, sh_ns;
     __shared__ double sh_acc[LS_THREADS / 32];
     __shared__ int sh_cell[TG_MAXK];
     const int b = blockIdx.y;
     const int F2 = F * F, cells = 3 * F2, nch = 5 + C;
     const int n = load_truth(labels, b, K, stride, tb, tcls, &sh_n);
     for (int t = threadIdx.x; t < n; t += LS_THREADS) sh_cell[t] = tcell_all[(size_t)b * K + t];
-    if (n > 0) prep_truth(n, tb, tc, tarea, tsimple);
+    if (n > 0) prep_truth(n, tb, tc, tarea, tns, tkey, &sh_ns);
     __syncthreads();
     const int cell = blockIdx.x * LS_THREADS + threadIdx.x;
     double term = 0.0;
@@ -165,7 +166,7 @@ k_loss_obj(const float *__restrict__ raw, const float *__restrict__ labels, int 
             // pred exactly as the train-mode YOLOLayer forms it (yololayer.py:126-134): grid units, no stride
             const float ax = __fadd_rn(spec_sigmoidf(t0), (float)i), ay = __fadd_rn(spec_sigmoidf(t1), (float)j);
             const float aw = __fmul_rn(spec_expf(t2), A.maw[a]), ah = __fmul_rn(spec_expf(t3), A.mah[a]);
-            ignored = iou_max_above(ax, ay, aw, ah, n, tb, tc, tarea, tsimple, ignore_thre);
+            ignored = iou_max_above(ax, ay, aw, ah, n, tb, tc, tarea, tns, sh_ns, ignore_thre);
         }
         const float x = spec_sigmoidf(t4);
         float g = 0.0f;

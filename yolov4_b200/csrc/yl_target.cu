@@ -37,10 +37,12 @@ k_target_objmask(const float *__restrict__ pred, long s0, long s1, long s2, long
     __shared__ __align__(16) float tc[TG_MAXK][4];       // GT corners (x1, y1, x2, y2) for the overlap pre-test
     __shared__ float tcls[TG_MAXK];
     __shared__ float tarea[TG_MAXK];
-    __shared__ unsigned char tsimple[TG_MAXK];
-    __shared__ int sh_n;
+    __shared__ unsigned char tns[TG_MAXK];
+    __shared__ float tkey[TG_MAXK];
+    __shared__ int sh_n, sh_ns;
     const int b = blockIdx.y;
     const int cells = 3 * F * F;
+    pdl_trigger();                                                    // k_target_scatter may load / match its labels meanwhile
     {
         // zero background of this CTA's cells (contiguous runs in all three tensors); k_target_scatter follows in stream order
         const int c0 = blockIdx.x * TG_THREADS;
@@ -56,18 +58,19 @@ k_target_objmask(const float *__restrict__ pred, long s0, long s1, long s2, long
         if (cell < cells) obj_mask[(size_t)b * cells + cell] = 1.0f;
         return;
     }
-    prep_truth(n, tb, tc, tarea, tsimple);
-    __syncthreads();
+    prep_truth(n, tb, tc, tarea, tns, tkey, &sh_ns);
     if (cell >= cells) return;
     const int a = cell / (F * F);
     const int r = cell - a * F * F;
     const int j = r / F, i = r - j * F;
     const float *pp = pred + (size_t)b * s0 + (size_t)a * s1 + (size_t)j * s2 + (size_t)i * s3;
     const float ax = pp[0], ay = pp[s4], aw = pp[2 * s4], ah = pp[3 * s4];
-    const bool best_above = iou_max_above(ax, ay, aw, ah, n, tb, tc, tarea, tsimple, ignore_thre);
+    const bool best_above = iou_max_above(ax, ay, aw, ah, n, tb, tc, tarea, tns, sh_ns, ignore_thre);
     obj_mask[(size_t)b * cells + cell] = best_above ? 0.0f : 1.0f;             // :286-294
 }
 
+
+constexpr int TS_SLICES = 4;
 
 __global__ void __launch_bounds__(TG_THREADS)
 k_target_scatter(const float *__restrict__ labels, int F, int K, int C, float stride, AnchorSet an,
@@ -79,6 +82,8 @@ k_target_scatter(const float *__restrict__ labels, int F, int K, int C, float st
     __shared__ int tcell[TG_MAXK];       // matched cell index within the image, or -1
     __shared__ int tanc[TG_MAXK];        // anchor slot a = best_n % 3
     __shared__ int sh_n;
+    // grid (B, TS_SLICES): every CTA matches all GTs of its image (the collision test needs them), slice y writes the
+    // cells of GTs t = y*8 + warp, + 8*TS_SLICES, ... so that an image's ~50 assignments are not one CTA's serial chain
     const int b = blockIdx.x;
     const int n = load_truth(labels, b, K, stride, tb, tcls, &sh_n);
     if (n == 0) return;
@@ -86,13 +91,14 @@ k_target_scatter(const float *__restrict__ labels, int F, int K, int C, float st
     const int cells = 3 * F * F;
     for (int t = threadIdx.x; t < n; t += TG_THREADS) {
         int anc;
-        const int cell = match_truth(tb[t], F, an, &anc, status);
+        const int cell = match_truth(tb[t], F, an, &anc, blockIdx.y == 0 ? status : nullptr);
         tcell[t] = cell;
         tanc[t] = anc;
     }
     __syncthreads();
+    pdl_wait();                                                       // zero background and ignore mask of k_target_objmask
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int t = warp; t < n; t += TG_THREADS / 32) {
+    for (int t = (int)blockIdx.y * (TG_THREADS / 32) + warp; t < n; t += (TG_THREADS / 32) * (int)gridDim.y) {
         const int cell = tcell[t];
         if (cell < 0) continue;
         const size_t gc = (size_t)b * cells + cell;
@@ -150,7 +156,7 @@ extern "C" int yl_build_target(const float *pred, const long *ps, const float *l
     k_target_objmask<<<grid, TG_THREADS, 0, st>>>(pred, ps[0], ps[1], ps[2], ps[3], ps[4], labels, F, K, C, stride, ignore_thre,
                                                   obj_mask, target, tgt_mask, tgt_scale);
     YL_LAUNCH_CHECK();
-    k_target_scatter<<<B, TG_THREADS, 0, st>>>(labels, F, K, C, stride, an, target, obj_mask, tgt_mask, tgt_scale, status);
-    YL_LAUNCH_CHECK();
+    YL_CUDA_TRY(launch_after(k_target_scatter, dim3(B, TS_SLICES), dim3(TG_THREADS), 0, st, pdl_enabled(), labels, F, K, C, stride, an,
+                             target, obj_mask, tgt_mask, tgt_scale, status));
     return YL_OK;
 }
