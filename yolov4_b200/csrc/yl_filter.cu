@@ -959,6 +959,9 @@ static const bool g_use_tma = !(getenv("YL_NO_TMA") && getenv("YL_NO_TMA")[0] ==
 // YL_FILTER selects the front-end form: "split" (default: lean streaming flag kernel + emit kernel),
 // "fused" (one kernel streams and emits: the TMA pipeline where planes are 16-byte aligned, register-staged otherwise).
 static const bool g_split = !(getenv("YL_FILTER") && strcmp(getenv("YL_FILTER"), "fused") == 0);
+// YL_FLAG_SMEM=<bytes, at most 48 KB>: dynamic shared memory requested (and not used) by k_flag_raw, which caps its CTAs per
+// SM so that CTAs of other kernels can be co-resident (cross-step pipelining experiments, tools/xstep_probe.py).
+static const int g_flag_smem = getenv("YL_FLAG_SMEM") ? atoi(getenv("YL_FLAG_SMEM")) : 0;
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda).
 static int encode_plane_map(CUtensorMap *map, const float *raw, int F2, long rows)
 {
@@ -1099,10 +1102,10 @@ static int filter_raw_impl(const float *const *raw, const int *F, int n_layers, 
         if (g_split) {
             if (stages & 1) {
                 switch (NW) {
-                case 1: k_flag_raw<1><<<grid, K1_THREADS, 0, st>>>(Pl); break;
-                case 2: k_flag_raw<2><<<grid, K1_THREADS, 0, st>>>(Pl); break;
-                case 3: k_flag_raw<3><<<grid, K1_THREADS, 0, st>>>(Pl); break;
-                default: k_flag_raw<4><<<grid, K1_THREADS, 0, st>>>(Pl); break;
+                case 1: k_flag_raw<1><<<grid, K1_THREADS, g_flag_smem, st>>>(Pl); break;
+                case 2: k_flag_raw<2><<<grid, K1_THREADS, g_flag_smem, st>>>(Pl); break;
+                case 3: k_flag_raw<3><<<grid, K1_THREADS, g_flag_smem, st>>>(Pl); break;
+                default: k_flag_raw<4><<<grid, K1_THREADS, g_flag_smem, st>>>(Pl); break;
                 }
                 YL_LAUNCH_CHECK();
             }

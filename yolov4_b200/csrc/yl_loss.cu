@@ -29,6 +29,13 @@ __device__ __forceinline__ float bce_term(float x, float t)
     const float lx = fmaxf(spec_logf(x), -100.0f), l1x = fmaxf(spec_logf(__fsub_rn(1.0f, x)), -100.0f);
     return __fsub_rn(__fmul_rn(__fsub_rn(t, 1.0f), l1x), __fmul_rn(t, lx));
 }
+// bce_term for t = 1 (one) or t = 0: the other logarithm is clamped to [-100, 0] and multiplied by zero, so the term is
+// -max(log x, -100) resp. -max(log(1 - x), -100) -- the same value (NaN included) for one spec_logf instead of two.
+__device__ __forceinline__ float bce_term01(float x, bool one)
+{
+    const float l = fmaxf(spec_logf(one ? x : __fsub_rn(1.0f, x)), -100.0f);
+    return __fsub_rn(0.0f, l);
+}
 __device__ __forceinline__ float bce_grad(float x, float t)
 {
     return __fdiv_rn(__fsub_rn(x, t), fmaxf(__fmul_rn(__fsub_rn(1.0f, x), x), 1e-12f));
@@ -145,11 +152,17 @@ k_loss_obj(const float *__restrict__ raw, const float *__restrict__ labels, int 
     __shared__ float tkey[TG_MAXK];
     __shared__ int sh_n, sh_ns;
     __shared__ double sh_acc[LS_THREADS / 32];
-    __shared__ int sh_cell[TG_MAXK];
+    __shared__ unsigned sh_hit[LS_THREADS / 32];
     const int b = blockIdx.y;
     const int F2 = F * F, cells = 3 * F2, nch = 5 + C;
     const int n = load_truth(labels, b, K, stride, tb, tcls, &sh_n);
-    for (int t = threadIdx.x; t < n; t += LS_THREADS) sh_cell[t] = tcell_all[(size_t)b * K + t];
+    // matched cells of this CTA's LS_THREADS consecutive cells as a bitmap (one lookup per cell instead of a scan of the GT list)
+    if (threadIdx.x < LS_THREADS / 32) sh_hit[threadIdx.x] = 0u;
+    __syncthreads();
+    for (int t = threadIdx.x; t < n; t += LS_THREADS) {
+        const int rel = tcell_all[(size_t)b * K + t] - (int)blockIdx.x * LS_THREADS;
+        if (rel >= 0 && rel < LS_THREADS) atomicOr(&sh_hit[rel >> 5], 1u << (rel & 31));
+    }
     if (n > 0) prep_truth(n, tb, tc, tarea, tns, tkey, &sh_ns);
     __syncthreads();
     const int cell = blockIdx.x * LS_THREADS + threadIdx.x;
@@ -159,20 +172,22 @@ k_loss_obj(const float *__restrict__ raw, const float *__restrict__ labels, int 
         const int j = r / F, i = r - j * F;
         const float *cp = raw + ((size_t)(b * 3 + a) * nch) * F2 + r;
         const float t0 = cp[0], t1 = cp[(size_t)F2], t2 = cp[2 * (size_t)F2], t3 = cp[3 * (size_t)F2], t4 = cp[4 * (size_t)F2];
-        bool matched = false;
-        for (int t = 0; t < n; ++t) matched |= (sh_cell[t] == cell);
+        const bool matched = (sh_hit[threadIdx.x >> 5] >> (threadIdx.x & 31)) & 1u;
         bool ignored = false;
         if (n > 0 && !matched) {                                       // :225-227: no labels => obj_mask stays 1
             // pred exactly as the train-mode YOLOLayer forms it (yololayer.py:126-134): grid units, no stride
-            const float ax = __fadd_rn(spec_sigmoidf(t0), (float)i), ay = __fadd_rn(spec_sigmoidf(t1), (float)j);
-            const float aw = __fmul_rn(spec_expf(t2), A.maw[a]), ah = __fmul_rn(spec_expf(t3), A.mah[a]);
+            float sx, sy, ew, eh;
+            spec_sigmoid2(t0, t1, sx, sy);                             // packed fp32x2 forms: the same bits as the scalar calls
+            spec_exp2(t2, t3, ew, eh);
+            const float ax = __fadd_rn(sx, (float)i), ay = __fadd_rn(sy, (float)j);
+            const float aw = __fmul_rn(ew, A.maw[a]), ah = __fmul_rn(eh, A.mah[a]);
             ignored = iou_max_above(ax, ay, aw, ah, n, tb, tc, tarea, tns, sh_ns, ignore_thre);
         }
         const float x = spec_sigmoidf(t4);
         float g = 0.0f;
         if (!ignored) {                                                // obj_mask = 1: BCE(x, t) with t = 1 on matched cells (:330,367,425)
             const float tg = matched ? 1.0f : 0.0f;
-            term = (double)bce_term(x, tg);
+            term = (double)bce_term01(x, matched);
             g = __fmul_rn(__fmul_rn(bce_grad(x, tg), x), __fsub_rn(1.0f, x));
         }
         gobj[(size_t)b * cells + cell] = g;
