@@ -38,6 +38,9 @@ typedef void *yl_stream_t; /* cudaStream_t */
 
 int yl_abi_version(void);
 const char *yl_error_string(int code);
+/* Self-test of the library's spec math (no reference counterpart): the bounded reciprocal used by the sigmoid against the
+ * IEEE quotient for every float in [1, 2^125]; *bad_dev (device u64) receives the number of mismatches. */
+int yl_selftest_rcp(unsigned long long *bad_dev, yl_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * A2  YOLOLayer.forward, eval branch                       replaces yolo/model/yololayer.py:88-120,146-166

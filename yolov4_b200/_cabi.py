@@ -34,6 +34,8 @@ def lib():
     L.yl_abi_version.argtypes = []
     L.yl_error_string.restype = ctypes.c_char_p
     L.yl_error_string.argtypes = [_i]
+    L.yl_selftest_rcp.restype = _i
+    L.yl_selftest_rcp.argtypes = [_p, _p]
     L.yl_decode_dense.restype = _i
     L.yl_decode_dense.argtypes = [_p, _i, _i, _i, _p, _f, _p, _l, _l, _p]
     L.yl_decode_train.restype = _i

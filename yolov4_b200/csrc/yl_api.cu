@@ -26,6 +26,31 @@ extern "C" const char *yl_error_string(int code)
     return "unknown error";
 }
 
+// Self-test of the spec math: rcp_rn_bounded(d) against __frcp_rn(d) (= the IEEE quotient 1.0f / d of the oracle) for every
+// float d in [1, 2^125]; *bad_dev receives the number of mismatches.
+namespace yl {
+__global__ void k_selftest_rcp(unsigned long long *bad)
+{
+    const unsigned lo = 0x3F800000u, hi = 0x7E000000u;              // 1.0f .. 2^125
+    unsigned long long n = 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x + lo; i <= hi;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const float d = __uint_as_float((unsigned)i);
+        n += (__float_as_uint(rcp_rn_bounded(d)) != __float_as_uint(__frcp_rn(d))) ? 1ull : 0ull;
+    }
+    if (n) atomicAdd(bad, n);
+}
+}  // namespace yl
+
+extern "C" int yl_selftest_rcp(unsigned long long *bad_dev, yl_stream_t stream)
+{
+    if (!bad_dev) return YL_ERR_ARG;
+    YL_CUDA_TRY(cudaMemsetAsync(bad_dev, 0, sizeof(unsigned long long), (cudaStream_t)stream));
+    yl::k_selftest_rcp<<<148 * 16, 256, 0, (cudaStream_t)stream>>>(bad_dev);
+    YL_LAUNCH_CHECK();
+    return YL_OK;
+}
+
 // -------------------------------------------------------------------------------------------------------------
 // Host-buffer path.  Images are independent (utils.py:133), so the batch is cut into groups: group g's H2D copy
 // runs on the copy stream while group g-1 is filtered and suppressed on the compute stream and the kept rows of
