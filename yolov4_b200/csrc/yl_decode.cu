@@ -43,10 +43,8 @@ k_decode_dense(const float *__restrict__ raw, int Fw, int F2, int C, float strid
                 t[u] = (k < nch) ? ldg_stream1(src + (size_t)k * F2) : 0.0f;
             }
             float sg[8];
-            if (kr >= 2) { sg[0] = spec_expf(t[0]); sg[1] = spec_sigmoidf(t[1]); }
-            else spec_sigmoid2(t[0], t[1], sg[0], sg[1]);
-#pragma unroll
-            for (int u = 2; u < 8; u += 2) spec_sigmoid2(t[u], t[u + 1], sg[u], sg[u + 1]);
+            spec_sigmoid_batch<8>(t, sg);                              // one range test for the batch
+            if (kr >= 2) sg[0] = spec_expf(t[0]);                       // tw / th
             float v0;
             if (kr == 0) v0 = __fmul_rn(__fadd_rn(sg[0], (float)gx), stride);
             else if (kr == 1) v0 = __fmul_rn(__fadd_rn(sg[0], (float)gy), stride);
@@ -68,8 +66,7 @@ k_decode_dense(const float *__restrict__ raw, int Fw, int F2, int C, float strid
                 t[u] = (k < nch) ? ldg_stream1(src + (size_t)k * F2) : 0.0f;
             }
             float sg[8];
-#pragma unroll
-            for (int u = 0; u < 8; u += 2) spec_sigmoid2(t[u], t[u + 1], sg[u], sg[u + 1]);
+            spec_sigmoid_batch<8>(t, sg);
             float *tp = tile + pl * nchp + k0;
 #pragma unroll
             for (int u = 0; u < 8; ++u)
@@ -110,8 +107,10 @@ k_decode_train(const float *__restrict__ raw, int Fw, int F2, int C, long total,
         t.load(raw + idx);
         float o[VEC];
         if (VEC == 4 && k != 2 && k != 3) {                                   // yololayer.py:105, two values per packed op
-            spec_sigmoid2(t.v[0], t.v[1 % VEC], o[0], o[1 % VEC]);
-            spec_sigmoid2(t.v[2 % VEC], t.v[3 % VEC], o[2 % VEC], o[3 % VEC]);
+            const float tt[4] = {t.v[0], t.v[1 % VEC], t.v[2 % VEC], t.v[3 % VEC]};
+            float ss[4];
+            spec_sigmoid_batch<4>(tt, ss);
+            o[0] = ss[0]; o[1 % VEC] = ss[1]; o[2 % VEC] = ss[2]; o[3 % VEC] = ss[3];
         } else {
 #pragma unroll
             for (int v = 0; v < VEC; ++v) o[v] = (k != 2 && k != 3) ? spec_sigmoidf(t.v[v]) : t.v[v];
