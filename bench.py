@@ -29,7 +29,7 @@ BYTES_PER_IMAGE = sum(3 * f * f for f in GRIDS) * (5 + C) * 4          # 7 732 6
 METRIC = "images/sec decode+NMS @608 b64 conf1e-4"
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_flag_raw<3> launch at B=64 from the ncu --set full capture in
 # profiles/
-TRAFFIC_PER_LAUNCH = 475215616 + 10545152   # profiles/r1_k_flag_raw_ncu_full_raw.csv
+TRAFFIC_PER_LAUNCH = 475235072 + 10179328   # profiles/r1_k_flag_raw_ncu_full_raw.csv
 UNIT = "images/s"
 
 
