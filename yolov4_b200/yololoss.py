@@ -2,8 +2,10 @@
 
 build_target(output, pred, layer_no, labels) -> (target, obj_mask, tgt_mask, tgt_scale)      (yololoss.py:118-371)
 forward(outputs, targets) restates the reference's loss arithmetic (yololoss.py:373-443) in plain torch so the
-class can replace the reference's criterion as a whole; that arithmetic is SURVEY.md's "next" row N2, not part of
-the accelerated path.
+class can replace the reference's criterion as a whole, dense tensors and all.
+fused_yolo_loss(head_outputs, padded_labels, cfg, ignore_thresh) is SURVEY.md's "next" row N2: the same loss value and
+its gradient with respect to the raw head tensors from yl_loss_forward / yl_loss_backward, without materialising
+output / pred / target / masks; the padded labels are cast and uploaded once for the three scales (row N4).
 """
 import numpy as np
 import torch
