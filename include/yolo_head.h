@@ -156,6 +156,10 @@ int yl_coco_rows(const float *rows, const int *row_image, long K, const double *
  *              class id outside [0, C) (the reference raises IndexError / writes another channel there); may be NULL
  * yl_loss_backward: grad_raw [B, 3*(5+C), F, F] = upstream[0] * d loss / d raw (upstream: device fp32 scalar).
  * None of the reference's dense output / pred / target / mask tensors is materialised: 5 of the 5+C planes are read.
+ * Aliasing rule: calls for different layers issued back to back on one stream overlap on the device (programmatic
+ * dependent launch: the next layer's matching runs in the tail of this layer's objectness kernel), so gobj / tcell_all /
+ * mcell / mgrad of consecutive calls must be distinct buffers (one set per layer, as yl_loss_backward needs anyway);
+ * loss4 and status are shared and only accumulated into.  YL_PDL=0 restores plain stream order.
  * --------------------------------------------------------------------------------------------------------- */
 int yl_loss_forward(const float *raw, const float *labels, int B, int F, int K, int C, int layer_no,
                     const float *anchors_px, const int *anchor_mask3, float ignore_thre,

@@ -27,6 +27,12 @@ t = yb.YOLOLoss(CFG, 0.7, device="cuda").build_target(d["output"], d["pred"], 1,
 w = orc.build_target(d["pred"].cpu().numpy(), labels.cpu().numpy(), 1, 80, 0.7)
 for a, b in zip(t, w):
     ok &= np.array_equal(a.cpu().numpy(), b, equal_nan=True)
+# fused loss, forward and backward (labels with a non-finite and a negative box: both branches of the ignore test)
+labels[0, 3, 2] = float("inf"); labels[1, 2, 2] = -9.0
+raws_g = [r.clone().requires_grad_(True) for r in raws]
+loss = yb.fused_yolo_loss(raws_g, labels, CFG, 0.7)
+loss.backward()
+ok &= bool(torch.isfinite(raws_g[0].grad).any().item())
 torch.cuda.synchronize()
 print("sanitize_small:", "ok" if ok else "MISMATCH")
 sys.exit(0 if ok else 1)

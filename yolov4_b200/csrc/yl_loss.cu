@@ -60,6 +60,7 @@ k_loss_match(const float *__restrict__ raw, const float *__restrict__ labels, in
     __shared__ int tcell[TG_MAXK];
     __shared__ int tanc[TG_MAXK];
     __shared__ int sh_n;
+    pdl_trigger();
     // grid (image, slice): every CTA of an image repeats the cheap assignment, then its warps take the GTs of its slice
     const int b = blockIdx.x;
     const int n = load_truth(labels, b, K, stride, tb, tcls, &sh_n);
@@ -138,6 +139,9 @@ k_loss_match(const float *__restrict__ raw, const float *__restrict__ labels, in
         if (acc_wh != 0.0) atomicAdd(&loss4[1], acc_wh);
         if (acc_cls != 0.0) atomicAdd(&loss4[3], acc_cls);
     }
+    // Nothing here reads the output of the kernel before it on the stream (the previous scale's k_loss_obj), so the
+    // two overlap; waiting at the end keeps completion ordered along the chain for whatever follows the last kernel.
+    pdl_wait();
 }
 
 __global__ void __launch_bounds__(LS_THREADS)
@@ -155,26 +159,21 @@ k_loss_obj(const float *__restrict__ raw, const float *__restrict__ labels, int 
     __shared__ unsigned sh_hit[LS_THREADS / 32];
     const int b = blockIdx.y;
     const int F2 = F * F, cells = 3 * F2, nch = 5 + C;
+    pdl_trigger();
     const int n = load_truth(labels, b, K, stride, tb, tcls, &sh_n);
-    // matched cells of this CTA's LS_THREADS consecutive cells as a bitmap (one lookup per cell instead of a scan of the GT list)
     if (threadIdx.x < LS_THREADS / 32) sh_hit[threadIdx.x] = 0u;
-    __syncthreads();
-    for (int t = threadIdx.x; t < n; t += LS_THREADS) {
-        const int rel = tcell_all[(size_t)b * K + t] - (int)blockIdx.x * LS_THREADS;
-        if (rel >= 0 && rel < LS_THREADS) atomicOr(&sh_hit[rel >> 5], 1u << (rel & 31));
-    }
     if (n > 0) prep_truth(n, tb, tc, tarea, tns, tkey, &sh_ns);
-    __syncthreads();
     const int cell = blockIdx.x * LS_THREADS + threadIdx.x;
     double term = 0.0;
+    float t4 = 0.0f;
+    bool ignored = false;
     if (cell < cells) {
         const int a = cell / F2, r = cell - a * F2;
         const int j = r / F, i = r - j * F;
         const float *cp = raw + ((size_t)(b * 3 + a) * nch) * F2 + r;
-        const float t0 = cp[0], t1 = cp[(size_t)F2], t2 = cp[2 * (size_t)F2], t3 = cp[3 * (size_t)F2], t4 = cp[4 * (size_t)F2];
-        const bool matched = (sh_hit[threadIdx.x >> 5] >> (threadIdx.x & 31)) & 1u;
-        bool ignored = false;
-        if (n > 0 && !matched) {                                       // :225-227: no labels => obj_mask stays 1
+        const float t0 = cp[0], t1 = cp[(size_t)F2], t2 = cp[2 * (size_t)F2], t3 = cp[3 * (size_t)F2];
+        t4 = cp[4 * (size_t)F2];
+        if (n > 0) {                                                   // :225-227: no labels => obj_mask stays 1
             // pred exactly as the train-mode YOLOLayer forms it (yololayer.py:126-134): grid units, no stride
             float sx, sy, ew, eh;
             spec_sigmoid2(t0, t1, sx, sy);                             // packed fp32x2 forms: the same bits as the scalar calls
@@ -183,6 +182,19 @@ k_loss_obj(const float *__restrict__ raw, const float *__restrict__ labels, int 
             const float aw = __fmul_rn(ew, A.maw[a]), ah = __fmul_rn(eh, A.mah[a]);
             ignored = iou_max_above(ax, ay, aw, ah, n, tb, tc, tarea, tns, sh_ns, ignore_thre);
         }
+    }
+    // Everything above is independent of k_loss_match (launched just before this kernel with programmatic dependent
+    // launch): only the matched cells need its output.  Bitmap of the matched cells among this CTA's LS_THREADS cells.
+    __syncthreads();
+    pdl_wait();
+    for (int t = threadIdx.x; t < n; t += LS_THREADS) {
+        const int rel = tcell_all[(size_t)b * K + t] - (int)blockIdx.x * LS_THREADS;
+        if (rel >= 0 && rel < LS_THREADS) atomicOr(&sh_hit[rel >> 5], 1u << (rel & 31));
+    }
+    __syncthreads();
+    if (cell < cells) {
+        const bool matched = (sh_hit[threadIdx.x >> 5] >> (threadIdx.x & 31)) & 1u;
+        if (matched) ignored = false;                                  // matched cells are never ignored (:330)
         const float x = spec_sigmoidf(t4);
         float g = 0.0f;
         if (!ignored) {                                                // obj_mask = 1: BCE(x, t) with t = 1 on matched cells (:330,367,425)
@@ -260,11 +272,14 @@ extern "C" int yl_loss_forward(const float *raw, const float *labels, int B, int
     LossAnchors A;
     const int rc = fill_anchors(A, anchors_px, anchor_mask3, stride);
     if (rc != YL_OK) return rc;
-    k_loss_match<<<dim3(B, 8), LS_THREADS, 0, st>>>(raw, labels, F, K, C, stride, A, loss4, tcell_all, mcell, mgrad, status);
-    YL_LAUNCH_CHECK();
+    // programmatic dependent launch along match(l) -> obj(l) -> match(l+1) -> ...: the latency-bound match kernels and the
+    // small scales' obj kernels fill the tails of their neighbours (see the waits in the kernels)
+    const bool pdl = pdl_enabled();
+    YL_CUDA_TRY(launch_after(k_loss_match, dim3(B, 8), dim3(LS_THREADS), 0, st, pdl, raw, labels, F, K, C, stride, A, loss4, tcell_all,
+                             mcell, mgrad, status));
     dim3 grid((3 * F * F + LS_THREADS - 1) / LS_THREADS, B);
-    k_loss_obj<<<grid, LS_THREADS, 0, st>>>(raw, labels, F, K, C, stride, A, ignore_thre, tcell_all, loss4, gobj);
-    YL_LAUNCH_CHECK();
+    YL_CUDA_TRY(launch_after(k_loss_obj, grid, dim3(LS_THREADS), 0, st, pdl, raw, labels, F, K, C, stride, A, ignore_thre,
+                             (const int *)tcell_all, loss4, gobj));
     return YL_OK;
 }
 

@@ -110,7 +110,7 @@ class _FusedYoloLoss(torch.autograd.Function):
         loss4 = torch.zeros(4, dtype=torch.float64, device=dev)
         status = torch.zeros(1, dtype=torch.int32, device=dev)
         anch = _cabi.floats([v for wh in anchors for v in wh])
-        saved = []
+        saved, keep = [], []
         with torch.cuda.device(dev):
             for l, r in enumerate(raws):
                 if not r.is_cuda or r.dtype != torch.float32 or r.dim() != 4 or r.shape[1] != 3 * (5 + C) or r.shape[0] != B:
@@ -125,6 +125,7 @@ class _FusedYoloLoss(torch.autograd.Function):
                                               float(np.float32(ignore_thresh)), loss4.data_ptr(), gobj.data_ptr(), tcell.data_ptr(),
                                               mcell.data_ptr(), mgrad.data_ptr(), status.data_ptr(), _stream()))
                 saved += [gobj, mcell, mgrad]
+                keep.append(tcell)          # see yl_loss_forward: the scales' kernels overlap, their buffers must not alias
         ctx.save_for_backward(*saved)
         ctx.shapes = [tuple(r.shape) for r in raws]
         ctx.K, ctx.C = K, C
@@ -168,6 +169,7 @@ def fused_yolo_loss_components(head_outputs, padded_labels, cfg, ignore_thresh=0
     loss4 = torch.zeros(4, dtype=torch.float64, device=dev)
     anch = _cabi.floats([v for wh in cfg['ANCHORS'] for v in wh])
     layers = list(range(len(head_outputs))) if layers is None else layers
+    keep = []                   # the scales' kernels overlap on the device (yl_loss_forward): no buffer is reused between them
     with torch.cuda.device(dev):
         for l, r in zip(layers, head_outputs):
             rc = r.detach().contiguous()
@@ -179,4 +181,5 @@ def fused_yolo_loss_components(head_outputs, padded_labels, cfg, ignore_thresh=0
             _cabi.check(L.yl_loss_forward(rc.data_ptr(), lab.data_ptr(), B, F, K, C, int(l), anch, _cabi.ints(cfg['ANCHOR_MASK'][l]),
                                           float(np.float32(ignore_thresh)), loss4.data_ptr(), gobj.data_ptr(), tcell.data_ptr(),
                                           mcell.data_ptr(), mgrad.data_ptr(), None, _stream()))
+            keep += [rc, gobj, tcell, mcell, mgrad]
     return loss4
