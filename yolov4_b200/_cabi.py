@@ -75,7 +75,7 @@ def lib():
 
 
 EXPORTS = [
-    "yl_abi_version", "yl_error_string", "yl_decode_dense", "yl_decode_train", "yl_decode_train_backward",
+    "yl_abi_version", "yl_error_string", "yl_selftest_rcp", "yl_decode_dense", "yl_decode_train", "yl_decode_train_backward",
     "yl_post_workspace_bytes", "yl_post_reset", "yl_filter_raw", "yl_filter_raw_stage", "yl_filter_dense", "yl_nms", "yl_build_target", "yl_coco_rows",
     "yl_loss_forward", "yl_loss_backward",
     "yl_context_create", "yl_context_destroy", "yl_detect_host",
