@@ -32,15 +32,21 @@ k_decode_dense(const float *__restrict__ raw, int Fw, int F2, int C, float strid
     if (pl < np) {
         const int p = p0 + pl;
         const int gy = p / Fw, gx = p - gy * Fw;
-        const float *src = raw + ((size_t)ba * nch) * F2 + p;
         constexpr int KR = DD_THREADS / DD_TP;                       // channel rows per pass
-        // first batch of eight channels (k = kr, kr+4, ...): slot 0 is one of tx, ty, tw, th; the others are obj / classes
+        // this thread's channels are kr, kr+KR, ...: one pointer walks them, eight loads per batch at constant plane strides;
+        // only the last batch of a row can be partial, so the full batches carry no per-load predicates or index arithmetic
+        const size_t rs = (size_t)KR * F2;
+        const float *q = raw + ((size_t)ba * nch + kr) * F2 + p;
+        float *tp = tile + pl * nchp + kr;
+        // first batch: slot 0 is one of tx, ty, tw, th; the others are obj / classes
         {
             float t[8];
+            if (kr + KR * 7 < nch) {
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int k = kr + KR * u;
-                t[u] = (k < nch) ? ldg_stream1(src + (size_t)k * F2) : 0.0f;
+                for (int u = 0; u < 8; ++u) t[u] = ldg_stream1(q + u * rs);
+            } else {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) t[u] = (kr + KR * u < nch) ? ldg_stream1(q + u * rs) : 0.0f;
             }
             float sg[8];
             spec_sigmoid_batch<8>(t, sg);                              // one range test for the batch
@@ -50,24 +56,28 @@ k_decode_dense(const float *__restrict__ raw, int Fw, int F2, int C, float strid
             else if (kr == 1) v0 = __fmul_rn(__fadd_rn(sg[0], (float)gy), stride);
             else if (kr == 2) v0 = __fmul_rn(__fmul_rn(sg[0], aw), stride);
             else v0 = __fmul_rn(__fmul_rn(sg[0], ah), stride);
-            float *tp = tile + pl * nchp + kr;
             tp[0] = v0;
 #pragma unroll
             for (int u = 1; u < 8; ++u)
                 if (kr + KR * u < nch) tp[KR * u] = sg[u];
         }
-        // the remaining batches are class channels only: two sigmoids per packed instruction stream
-        // (spec_sigmoid2: same bits as the scalar form), no per-channel case analysis
-        for (int k0 = kr + KR * 8; k0 < nch; k0 += KR * 8) {         // eight loads in flight per thread, then the math
-            float t[8];
+        // the remaining batches are class channels only
+        int k0 = kr + KR * 8;
+        q += 8 * rs;
+        tp += KR * 8;
+        for (; k0 + KR * 7 < nch; k0 += KR * 8, q += 8 * rs, tp += KR * 8) {
+            float t[8], sg[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int k = k0 + KR * u;
-                t[u] = (k < nch) ? ldg_stream1(src + (size_t)k * F2) : 0.0f;
-            }
-            float sg[8];
+            for (int u = 0; u < 8; ++u) t[u] = ldg_stream1(q + u * rs);
             spec_sigmoid_batch<8>(t, sg);
-            float *tp = tile + pl * nchp + k0;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) tp[KR * u] = sg[u];
+        }
+        if (k0 < nch) {
+            float t[8], sg[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) t[u] = (k0 + KR * u < nch) ? ldg_stream1(q + u * rs) : 0.0f;
+            spec_sigmoid_batch<8>(t, sg);
 #pragma unroll
             for (int u = 0; u < 8; ++u)
                 if (k0 + KR * u < nch) tp[KR * u] = sg[u];
