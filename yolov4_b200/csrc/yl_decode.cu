@@ -99,36 +99,39 @@ k_decode_dense(const float *__restrict__ raw, int Fw, int F2, int C, float strid
 
 constexpr int DT_THREADS = 256;
 
+// One CTA per plane (image, anchor, channel): the channel's case analysis is CTA-uniform and no thread divides a 64-bit
+// element index by F*F / (5+C) (the grid-stride form spent more instructions on that than on the spec math).
 template <int VEC>
 __global__ void __launch_bounds__(DT_THREADS)
-k_decode_train(const float *__restrict__ raw, int Fw, int F2, int C, long total,
+k_decode_train(const float *__restrict__ raw, int Fw, int F2, int C,
                float aw0, float ah0, float aw1, float ah1, float aw2, float ah2,
                float *__restrict__ output_planar, float *__restrict__ pred_planar)
 {
     const int nch = 5 + C;
-    const long nvec = total / VEC;
-    for (long iv = (long)blockIdx.x * DT_THREADS + threadIdx.x; iv < nvec; iv += (long)gridDim.x * DT_THREADS) {
-        const long idx = iv * VEC;                                            // VEC consecutive elements of one plane
-        const long plane = idx / F2;
-        const int p = (int)(idx - plane * F2);
-        const int ba = (int)(plane / nch);
-        const int k = (int)(plane - (long)ba * nch);
+    const unsigned plane = blockIdx.x;
+    const int ba = (int)(plane / (unsigned)nch);
+    const int k = (int)(plane - (unsigned)ba * (unsigned)nch);
+    const int a = ba % 3;
+    const size_t base = (size_t)plane * F2;
+    const bool sig = (k != 2 && k != 3);                                      // yololayer.py:105
+    const float anc = (k == 2) ? ((a == 0) ? aw0 : ((a == 1) ? aw1 : aw2)) : ((a == 0) ? ah0 : ((a == 1) ? ah1 : ah2));
+    float *pdst = pred_planar + ((size_t)ba * 4 + (k < 4 ? k : 0)) * F2;
+    for (int p = threadIdx.x * VEC; p < F2; p += DT_THREADS * VEC) {
         Vec<VEC> t;
-        t.load(raw + idx);
+        t.load(raw + base + p);
         float o[VEC];
-        if (VEC == 4 && k != 2 && k != 3) {                                   // yololayer.py:105, two values per packed op
+        if (VEC == 4 && sig) {                                                // two values per packed op, one range test
             const float tt[4] = {t.v[0], t.v[1 % VEC], t.v[2 % VEC], t.v[3 % VEC]};
             float ss[4];
             spec_sigmoid_batch<4>(tt, ss);
             o[0] = ss[0]; o[1 % VEC] = ss[1]; o[2 % VEC] = ss[2]; o[3 % VEC] = ss[3];
         } else {
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) o[v] = (k != 2 && k != 3) ? spec_sigmoidf(t.v[v]) : t.v[v];
+            for (int v = 0; v < VEC; ++v) o[v] = sig ? spec_sigmoidf(t.v[v]) : t.v[v];
         }
-        if (VEC == 4) *reinterpret_cast<float4 *>(output_planar + idx) = make_float4(o[0], o[1 % VEC], o[2 % VEC], o[3 % VEC]);
-        else output_planar[idx] = o[0];
+        if (VEC == 4) *reinterpret_cast<float4 *>(output_planar + base + p) = make_float4(o[0], o[1 % VEC], o[2 % VEC], o[3 % VEC]);
+        else output_planar[base + p] = o[0];
         if (k < 4) {
-            const int a = ba % 3;
             float pv[VEC], ex[VEC];
             if (k >= 2) {
                 if (VEC == 4) { spec_exp2(t.v[0], t.v[1 % VEC], ex[0], ex[1 % VEC]); spec_exp2(t.v[2 % VEC], t.v[3 % VEC], ex[2 % VEC], ex[3 % VEC]); }
@@ -139,34 +142,32 @@ k_decode_train(const float *__restrict__ raw, int Fw, int F2, int C, long total,
                 const int pp = p + v;
                 if (k == 0) pv[v] = __fadd_rn(o[v], (float)(pp % Fw));                   // :126
                 else if (k == 1) pv[v] = __fadd_rn(o[v], (float)(pp / Fw));              // :129
-                else if (k == 2) pv[v] = __fmul_rn(ex[v], (a == 0) ? aw0 : ((a == 1) ? aw1 : aw2));               // :132
-                else pv[v] = __fmul_rn(ex[v], (a == 0) ? ah0 : ((a == 1) ? ah1 : ah2));                           // :134
+                else pv[v] = __fmul_rn(ex[v], anc);                                      // :132, :134
             }
-            float *dst = pred_planar + ((size_t)ba * 4 + k) * F2 + p;
-            if (VEC == 4) *reinterpret_cast<float4 *>(dst) = make_float4(pv[0], pv[1 % VEC], pv[2 % VEC], pv[3 % VEC]);
-            else dst[0] = pv[0];
+            if (VEC == 4) *reinterpret_cast<float4 *>(pdst + p) = make_float4(pv[0], pv[1 % VEC], pv[2 % VEC], pv[3 % VEC]);
+            else pdst[p] = pv[0];
         }
     }
 }
 
 template <int VEC>
 __global__ void __launch_bounds__(DT_THREADS)
-k_decode_train_bwd(const float *__restrict__ output_planar, const float *__restrict__ grad_out, int F2, int C, long total,
+k_decode_train_bwd(const float *__restrict__ output_planar, const float *__restrict__ grad_out, int F2, int C,
                    float *__restrict__ grad_raw)
 {
     const int nch = 5 + C;
-    const long nvec = total / VEC;
-    for (long iv = (long)blockIdx.x * DT_THREADS + threadIdx.x; iv < nvec; iv += (long)gridDim.x * DT_THREADS) {
-        const long idx = iv * VEC;
-        const int k = (int)((idx / F2) % nch);
+    const unsigned plane = blockIdx.x;
+    const int k = (int)(plane % (unsigned)nch);
+    const size_t base = (size_t)plane * F2;
+    for (int p = threadIdx.x * VEC; p < F2; p += DT_THREADS * VEC) {
         Vec<VEC> g, o;
-        g.load(grad_out + idx);
-        o.load(output_planar + idx);
+        g.load(grad_out + base + p);
+        o.load(output_planar + base + p);
         float r[VEC];
 #pragma unroll
         for (int v = 0; v < VEC; ++v) r[v] = (k == 2 || k == 3) ? g.v[v] : (g.v[v] * (1.0f - o.v[v])) * o.v[v];     // ATen sigmoid_backward order
-        if (VEC == 4) *reinterpret_cast<float4 *>(grad_raw + idx) = make_float4(r[0], r[1 % VEC], r[2 % VEC], r[3 % VEC]);
-        else grad_raw[idx] = r[0];
+        if (VEC == 4) *reinterpret_cast<float4 *>(grad_raw + base + p) = make_float4(r[0], r[1 % VEC], r[2 % VEC], r[3 % VEC]);
+        else grad_raw[base + p] = r[0];
     }
 }
 
@@ -197,17 +198,16 @@ extern "C" int yl_decode_train(const float *raw, int B, int F, int C, const floa
 {
     if (!raw || !ag || !output_planar || !pred_planar || B <= 0 || F <= 0 || C <= 0) return YL_ERR_ARG;
     const int F2 = F * F;
-    const long total = (long)B * 3 * (5 + C) * F2;
+    const long planes = (long)B * 3 * (5 + C);
+    if (planes > 0x7FFFFFFFL) return YL_ERR_ARG;
     // planes are 16-byte aligned when F*F is a multiple of 4 and the bases are: then four elements per thread
     const bool vec4 = (F2 % 4 == 0) && (((uintptr_t)raw | (uintptr_t)output_planar | (uintptr_t)pred_planar) % 16 == 0);
-    const long blocks = (total / (vec4 ? 4 : 1) + DT_THREADS - 1) / DT_THREADS;
-    const int grid = (int)(blocks < 148L * 64 ? blocks : 148L * 64);
     if (vec4)
-        k_decode_train<4><<<grid, DT_THREADS, 0, (cudaStream_t)stream>>>(raw, F, F2, C, total, ag[0], ag[1], ag[2], ag[3], ag[4],
-                                                                         ag[5], output_planar, pred_planar);
+        k_decode_train<4><<<(unsigned)planes, DT_THREADS, 0, (cudaStream_t)stream>>>(raw, F, F2, C, ag[0], ag[1], ag[2], ag[3], ag[4],
+                                                                                   ag[5], output_planar, pred_planar);
     else
-        k_decode_train<1><<<grid, DT_THREADS, 0, (cudaStream_t)stream>>>(raw, F, F2, C, total, ag[0], ag[1], ag[2], ag[3], ag[4],
-                                                                         ag[5], output_planar, pred_planar);
+        k_decode_train<1><<<(unsigned)planes, DT_THREADS, 0, (cudaStream_t)stream>>>(raw, F, F2, C, ag[0], ag[1], ag[2], ag[3], ag[4],
+                                                                                   ag[5], output_planar, pred_planar);
     YL_LAUNCH_CHECK();
     return YL_OK;
 }
@@ -217,12 +217,11 @@ extern "C" int yl_decode_train_backward(const float *output_planar, const float 
 {
     if (!output_planar || !grad_out_planar || !grad_raw || B <= 0 || F <= 0 || C <= 0) return YL_ERR_ARG;
     const int F2 = F * F;
-    const long total = (long)B * 3 * (5 + C) * F2;
+    const long planes = (long)B * 3 * (5 + C);
+    if (planes > 0x7FFFFFFFL) return YL_ERR_ARG;
     const bool vec4 = (F2 % 4 == 0) && (((uintptr_t)output_planar | (uintptr_t)grad_out_planar | (uintptr_t)grad_raw) % 16 == 0);
-    const long blocks = (total / (vec4 ? 4 : 1) + DT_THREADS - 1) / DT_THREADS;
-    const int grid = (int)(blocks < 148L * 64 ? blocks : 148L * 64);
-    if (vec4) k_decode_train_bwd<4><<<grid, DT_THREADS, 0, (cudaStream_t)stream>>>(output_planar, grad_out_planar, F2, C, total, grad_raw);
-    else k_decode_train_bwd<1><<<grid, DT_THREADS, 0, (cudaStream_t)stream>>>(output_planar, grad_out_planar, F2, C, total, grad_raw);
+    if (vec4) k_decode_train_bwd<4><<<(unsigned)planes, DT_THREADS, 0, (cudaStream_t)stream>>>(output_planar, grad_out_planar, F2, C, grad_raw);
+    else k_decode_train_bwd<1><<<(unsigned)planes, DT_THREADS, 0, (cudaStream_t)stream>>>(output_planar, grad_out_planar, F2, C, grad_raw);
     YL_LAUNCH_CHECK();
     return YL_OK;
 }
