@@ -114,6 +114,27 @@ def cpu_baseline(sample_images, threads, seed=0, min_seconds=0.0):
     return sample_images * passes / dt, dt, rows, passes
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """stdout must carry exactly one JSON line: from here on everything written to file descriptor 1 (NCCL's version banner,
+    library chatter of any rank) lands on stderr, and emit() writes the line to the real stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -139,7 +160,7 @@ def run_reference(args, rank, world):
                                    "OpenMP over images" % per_step},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
@@ -154,6 +175,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=64, help="images timed for the CPU baseline (0 = skip)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="repeat the CPU sample until this much time is spent")
     args = ap.parse_args()
+    claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -161,9 +183,6 @@ def main():
         run_reference(args, rank, world)
         return
     args.warmup = max(args.warmup, 3)
-    # stdout carries exactly one JSON line: keep NCCL's version banner off it
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"
 
     import torch
     import torch.distributed as dist
@@ -305,7 +324,7 @@ def main():
             "cpu_baseline": cpu,
             "clocks": clocks,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
