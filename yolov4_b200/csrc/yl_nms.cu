@@ -679,6 +679,13 @@ k_gather_rows(const uint4 *__restrict__ cand, const unsigned *__restrict__ seg_c
     const int seg = seg_first + blockIdx.x;
     const int b = seg / C, c = seg - b * C;
     const int tid = threadIdx.x;
+    // the first 2 x 128 float4s of the segment's finished rows (4 KB, the typical segment) are requested before the kept
+    // counts are known, so the copy's round trip overlaps the prefix's instead of following it
+    const float4 *src4 = reinterpret_cast<const float4 *>(cand + (size_t)seg * cap_seg * 2);
+    const unsigned lim4 = (unsigned)cap_seg * 2u;
+    float4 spec0 = make_float4(0.f, 0.f, 0.f, 0.f), spec1 = spec0;
+    if ((unsigned)tid < lim4) spec0 = src4[tid];
+    if ((unsigned)tid + GATHER_THREADS < lim4) spec1 = src4[tid + GATHER_THREADS];
     // exclusive prefix of kept counts over lower classes; class 0 also reduces the candidate statistics
     unsigned pre = 0u, mx = 0u, tot = 0u;
     for (int k = tid; k < C; k += GATHER_THREADS) {
@@ -706,9 +713,8 @@ k_gather_rows(const uint4 *__restrict__ cand, const unsigned *__restrict__ seg_c
     float *dst = out_rows + ((size_t)b * cap_out + pre) * 7;
     // the source run is 16-byte aligned, the destination only 4-byte: 128-bit loads, scalar stores
     const unsigned nf = nwr * 7u, nf4 = nf >> 2;
-    const float4 *src4 = reinterpret_cast<const float4 *>(src);
     for (unsigned i = tid; i < nf4; i += GATHER_THREADS) {
-        const float4 v = src4[i];
+        const float4 v = (i == (unsigned)tid) ? spec0 : ((i == (unsigned)tid + GATHER_THREADS) ? spec1 : src4[i]);
         float *d = dst + 4 * i;
         d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
     }
