@@ -70,3 +70,19 @@ def test_synth_generator_is_seeded_and_shaped():
     assert all(torch.equal(x, y) for x, y in zip(a, b))
     lab = synth_labels(3, 608, n_valid=50)
     assert lab.shape == (3, 60, 5) and (lab[:, 50:] == 0).all() and (lab[:, :50, 2:4] > 0).all()
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    """The driver parses stdout of bench.py: one JSON line, nothing else (library banners go to stderr)."""
+    import json
+    import subprocess
+    import sys
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--cpu-seconds", "0.5"], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [l for l in p.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, p.stdout[:2000]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "images/s" and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
