@@ -310,7 +310,7 @@ def main():
             "config": {"workload": "yolov4 head outputs batch %d/GPU @608x608 (grids 76/38/19), 80 classes, conf 1e-4, nms 0.4 "
                                    "(BASELINE configs[1])" % B,
                        "l2": "inputs (495 MB/step) are larger than L2 (126 MB); no flush needed",
-                       "timed": "CUDA-graph replay of counter reset + k_flag_raw + k_emit_flagged + k_segment_nms_bins + k_segment_nms_big + k_gather_rows",
+                       "timed": "CUDA-graph replay of k_flag_raw (also zeroes the workspace counters) + k_emit_flagged + k_segment_nms_bins + k_segment_nms_big + k_gather_rows",
                        "rows_per_step": rows_per_step, "parallelism": "images sharded by rank, no collective on the hot path",
                        "final_allgather_ms": gather_ms},
             "gpu_launches": hp.launches_per_run * args.steps,

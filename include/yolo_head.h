@@ -101,7 +101,9 @@ int yl_filter_raw(const float *const *raw, const int *F, int n_layers, int B, in
                   yl_stream_t stream);
 
 /* The two kernels of yl_filter_raw run separately (measurement / pipelining): stages bit 0 = streaming flag kernel
- * (reads every raw byte once, writes 16 B per box), bit 1 = emit kernel (resolves the flagged pairs exactly). */
+ * (reads every raw byte once, writes 16 B per box), bit 1 = emit kernel (resolves the flagged pairs exactly).
+ * Bit 2 (with bit 0 or 1): the call also resets the workspace counters, i.e. it replaces yl_post_reset -- inside the flag
+ * kernel where that exists, so a step has one graph node less; only for the first (or only) image group of a step. */
 int yl_filter_raw_stage(const float *const *raw, const int *F, int n_layers, int B, int C,
                         const float *anchors_px, const int *anchor_mask, float conf_thre,
                         void *ws, size_t ws_bytes, long M, int cap_seg, int img_first, int img_count,

@@ -54,6 +54,8 @@ struct RawParams {
     RawLayer layer[3];
     int n_layers, C, cap_seg, img_first;
     int sparse;            // high thresholds: look at the objectness plane first and skip the class planes of dead vectors
+    unsigned *reset;       // stages bit 2: the counters of the workspace, zeroed by the flag kernel itself (no memset node)
+    int reset_words;
     long M;
     float thr;
     uint4 *cand;
@@ -452,6 +454,11 @@ __global__ void __launch_bounds__(K1_THREADS, YL_FLAG_MINB)
 k_flag_raw(const __grid_constant__ RawParams P)
 {
     pdl_trigger();
+    if (P.reset_words > 0 && blockIdx.y == 0) {
+        // yl_post_reset folded into this kernel: nothing reads the counters before the emit kernel, which waits for this
+        // grid to complete
+        for (int i = blockIdx.x * K1_THREADS + threadIdx.x; i < P.reset_words; i += gridDim.x * K1_THREADS) P.reset[i] = 0u;
+    }
     const int ba = P.img_first * 3 + blockIdx.y;
     int tile = blockIdx.x;
     int l = 0;
@@ -1027,6 +1034,12 @@ static int filter_raw_impl(const float *const *raw, const int *F, int n_layers, 
     base.sparse = conf_thre >= 0.02f ? 1 : 0;     // sigmoid(obj) >= 0.02 is rare for background cells (obj logit >= -3.9)
     base.cand = cand; base.seg_count = seg_count; base.objtab = objtab; base.n_layers = 0;
     base.flags = (unsigned *)(w + L.off_flags); base.M4 = L.M4; base.BM4 = (long)B * L.M4;
+    base.reset = (unsigned *)w; base.reset_words = 0;
+    if (stages & 4) {
+        // the caller skips yl_post_reset: the split form's flag kernel zeroes the counters, every other form gets a memset
+        if (g_split && (stages & 1)) base.reset_words = (int)(L.counters_bytes / sizeof(unsigned));
+        else YL_CUDA_TRY(cudaMemsetAsync(ws, 0, L.counters_bytes, (cudaStream_t)stream));
+    }
     RawParams Pt = base, Pl = base;                 // Pt: persistent TMA kernel (TMA scales first, scalar scales last); Pl: LDG kernel
     RawLayer lay[3];
     int row_off = 0, tiles_tma = 0, tiles_ldg = 0, n_tma = 0;
@@ -1147,7 +1160,7 @@ extern "C" int yl_filter_raw_stage(const float *const *raw, const int *F, int n_
                                    void *ws, size_t ws_bytes, long M, int cap_seg, int img_first, int img_count,
                                    int stages, yl_stream_t stream)
 {
-    if (stages < 1 || stages > 3) return YL_ERR_ARG;
+    if (stages < 1 || stages > 7 || (stages & 3) == 0) return YL_ERR_ARG;
     return filter_raw_impl(raw, F, n_layers, B, C, anchors_px, anchor_mask, conf_thre, ws, ws_bytes, M, cap_seg, img_first,
                            img_count, stream, stages);
 }

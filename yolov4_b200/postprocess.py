@@ -214,11 +214,17 @@ class HeadPostprocessor:
         L, B, C, M = self.L, self.B, self.C, self.M
         rp = _cabi.ptrs([r.data_ptr() for r in head_outputs])
         main = torch.cuda.current_stream(self.device)
-        _cabi.check(L.yl_post_reset(self.ws.ptr(), self.ws.nbytes, B, M, C, self.cap_seg, main.cuda_stream))
         G = self.n_groups
+        fold_reset = (G == 1 and self.mode != "emit_side")    # one group: the flag kernel zeroes the counters itself
+        if not fold_reset:
+            _cabi.check(L.yl_post_reset(self.ws.ptr(), self.ws.nbytes, B, M, C, self.cap_seg, main.cuda_stream))
         for g in range(G):
             i0, i1 = B * g // G, B * (g + 1) // G
-            if self.mode == "emit_side":
+            if fold_reset:
+                _cabi.check(L.yl_filter_raw_stage(rp, self.fs, len(self.Fs), B, C, self.anch, self.mask, self.conf, self.ws.ptr(),
+                                                  self.ws.nbytes, M, self.cap_seg, i0, i1 - i0, 7, main.cuda_stream))
+                self.side.wait_stream(main)
+            elif self.mode == "emit_side":
                 # streaming flag kernels back to back on the main stream; everything else follows on the side stream
                 _cabi.check(L.yl_filter_raw_stage(rp, self.fs, len(self.Fs), B, C, self.anch, self.mask, self.conf, self.ws.ptr(),
                                                   self.ws.nbytes, M, self.cap_seg, i0, i1 - i0, 1, main.cuda_stream))
