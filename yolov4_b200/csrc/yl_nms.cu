@@ -121,6 +121,9 @@ constexpr int QCAP_W = YL_NMS_QCAP;                     // queued pairs per warp
 #ifndef YL_NMS_MINB
 #define YL_NMS_MINB 10
 #endif
+#ifndef YL_NMS_SPLIT_RANK
+#define YL_NMS_SPLIT_RANK 1
+#endif
 constexpr int AREA_BIN_OFF = (127 + 4) << 2;            // float bits >> 21 of 16.0f: areas below 16 px^2 share bin 0
 
 struct alignas(16) BinsSmem {
@@ -255,10 +258,34 @@ k_segment_nms_bins(uint4 *__restrict__ cand, const unsigned *__restrict__ seg_co
     const int wbase = tid & ~31;                                // warp-uniform bounds below
     int rank[SMALL_EPT];
 #pragma unroll
-    for (int u = 0; u < SMALL_EPT; ++u) {
-        rank[u] = 0;
-        if (wbase + u * SMALL_THREADS < n) rank[u] = rank32(S.a.s.key, n, key[u]);
+    for (int u = 0; u < SMALL_EPT; ++u) rank[u] = 0;
+    if (wbase < n) rank[0] = rank32(S.a.s.key, n, key[0]);
+#if YL_NMS_SPLIT_RANK
+    static_assert(SMALL_EPT == 2, "the split second pass assumes two records per thread");
+    if (n > SMALL_THREADS) {                                    // CTA-uniform
+        // Records SMALL_THREADS.. (a few dozen in the typical segment of ~144) would all sit in warp 0 and make it walk
+        // every key a second time while the other warps wait at the barrier.  Instead every warp ranks them against its own
+        // quarter of the keys and the partial counts are added up in shared memory.
+        const int x = n - SMALL_THREADS;
+        S.bins[tid] = 0u;                                       // S.bins is free until the sorted arrays are built
+        __syncthreads();
+        const int n4 = (n + 3) >> 2;
+        const int g0 = (n4 * warp) / SMALL_WARPS, g1 = (n4 * (warp + 1)) / SMALL_WARPS;
+        for (int c = 0; 32 * c < x; ++c) {
+            const int i = 32 * c + lane;
+            if (i < x) {
+                const int part = rank32(S.a.s.key + 4 * g0, 4 * (g1 - g0), S.a.s.key[SMALL_THREADS + i]);
+                atomicAdd(&S.bins[i], (unsigned)part);
+            }
+        }
+        __syncthreads();
+        if (tid < x) rank[1] = (int)S.bins[tid];
     }
+#else
+#pragma unroll
+    for (int u = 1; u < SMALL_EPT; ++u)
+        if (wbase + u * SMALL_THREADS < n) rank[u] = rank32(S.a.s.key, n, key[u]);
+#endif
 #pragma unroll
     for (int u = 0; u < SMALL_EPT; ++u) {
         const int e = tid + u * SMALL_THREADS;
