@@ -358,17 +358,40 @@ k_segment_nms_bins(uint4 *__restrict__ cand, const unsigned *__restrict__ seg_co
         }
     }
     __syncthreads();
-    // prefix / suffix OR over the bins: 6 tables x nwp word pairs, one lane per chain (direction by index arithmetic,
-    // so the lanes of both directions run the same instruction stream)
-    if (tid < 6 * (SMALL_W / 2)) {
-        const int t = tid >> 2, wp = tid & 3;
-        if (wp < nwp) {
+    // prefix / suffix OR over the bins of 6 tables x nwp word pairs.  Eight lanes share a chain: each ORs its own run of
+    // bins (independent loads), a 3-step shuffle scan over the eight run totals gives every lane its carry, and the runs
+    // are stored back -- about 15 dependent steps where one lane per chain walked NBIN of them while three warps waited.
+    {
+        constexpr int BPL = (NBIN + 7) / 8;                     // bins per lane
+        const int nchain = 6 * nwp;
+        const int sub = tid & 7;
+        for (int c0 = 0; c0 < nchain; c0 += SMALL_THREADS / 8) {    // CTA-uniform trip count: the shuffles run with a full mask
+            const int c = c0 + (tid >> 3);
+            const bool valid = c < nchain;
+            const int t = valid ? c / nwp : 0, wp = valid ? c - t * nwp : 0;
             unsigned long long *p = &S.b.tab[t][wp][0];
-            const int step = (t & 1) ? 1 : -1;
-            int pos = (t & 1) ? 0 : NBIN - 1;
-            unsigned long long acc = 0ull;
-#pragma unroll 8
-            for (int i = 0; i < NBIN; ++i, pos += step) { acc |= p[pos]; p[pos] = acc; }
+            const bool fwd = (t & 1) != 0;                      // odd tables are prefix sets, even ones suffix sets
+            unsigned long long v[BPL];
+#pragma unroll
+            for (int k = 0; k < BPL; ++k) {
+                const int i = BPL * sub + k;                    // position along the scan direction
+                v[k] = (valid && i < NBIN) ? p[fwd ? i : NBIN - 1 - i] : 0ull;
+            }
+#pragma unroll
+            for (int k = 1; k < BPL; ++k) v[k] |= v[k - 1];
+            unsigned long long incl = v[BPL - 1];
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) {
+                const unsigned long long y = __shfl_up_sync(FULL, incl, o, 8);
+                if (sub >= o) incl |= y;
+            }
+            unsigned long long carry = __shfl_up_sync(FULL, incl, 1, 8);
+            if (sub == 0) carry = 0ull;
+#pragma unroll
+            for (int k = 0; k < BPL; ++k) {
+                const int i = BPL * sub + k;
+                if (valid && i < NBIN) p[fwd ? i : NBIN - 1 - i] = v[k] | carry;
+            }
         }
     }
     __syncthreads();
