@@ -37,6 +37,8 @@ extern "C" {
 typedef void *yl_stream_t; /* cudaStream_t */
 
 int yl_abi_version(void);
+/* Hash of the sources the library was compiled from (build.py:source_hash); the loader refuses a stale library. */
+const char *yl_source_hash(void);
 const char *yl_error_string(int code);
 /* Self-test of the library's spec math (no reference counterpart): the bounded reciprocal used by the sigmoid against the
  * IEEE quotient for every float in [1, 2^125]; *bad_dev (device u64) receives the number of mismatches. */
@@ -65,6 +67,11 @@ int yl_decode_train(const float *raw, int B, int F, int C, const float *anch_gri
                     float *output_planar, float *pred_planar, yl_stream_t stream);
 int yl_decode_train_backward(const float *output_planar, const float *grad_out_planar, int B, int F, int C,
                              float *grad_raw, yl_stream_t stream);
+/* The same gradient from the RAW head tensor (sigmoid recomputed with the bits of the forward pass).  This is the form the
+ * autograd node uses: the reference's YOLOLoss.forward multiplies dict['output'] by its masks in place
+ * (yololoss.py:402-408), so the tensor the forward returned cannot be the one kept for the backward pass. */
+int yl_decode_train_backward_raw(const float *raw, const float *grad_out_planar, int B, int F, int C,
+                                 float *grad_raw, yl_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * A4+A5  postprocess(prediction, num_classes, conf_thre, nms_thre)   replaces yolo/util/utils.py:92-223
@@ -158,12 +165,21 @@ int yl_coco_rows(const float *rows, const int *row_image, long K, const double *
  *              class id outside [0, C) (the reference raises IndexError / writes another channel there); may be NULL
  * yl_loss_backward: grad_raw [B, 3*(5+C), F, F] = upstream[0] * d loss / d raw (upstream: device fp32 scalar).
  * None of the reference's dense output / pred / target / mask tensors is materialised: 5 of the 5+C planes are read.
- * Aliasing rule: calls for different layers issued back to back on one stream overlap on the device (programmatic
- * dependent launch: the next layer's matching runs in the tail of this layer's objectness kernel), so gobj / tcell_all /
+ * Aliasing rule: calls for different layers issued back to back on one stream (yl_loss_forward_chained) overlap on the device
+ * (programmatic dependent launch: the next layer's matching runs in the tail of this layer's objectness kernel), so gobj / tcell_all /
  * mcell / mgrad of consecutive calls must be distinct buffers (one set per layer, as yl_loss_backward needs anyway);
  * loss4 and status are shared and only accumulated into.  YL_PDL=0 restores plain stream order.
  * --------------------------------------------------------------------------------------------------------- */
 int yl_loss_forward(const float *raw, const float *labels, int B, int F, int K, int C, int layer_no,
+                    const float *anchors_px, const int *anchor_mask3, float ignore_thre,
+                    double *loss4, float *gobj, int *tcell_all, int *mcell, float *mgrad, int *status,
+                    yl_stream_t stream);
+/* The same call for the SECOND and later layers of one loss evaluation, issued directly behind the previous layer's
+ * yl_loss_forward[_chained] on the same stream: its matching kernel is launched programmatically and starts in the tail of
+ * the previous layer's objectness kernel.  It reads raw / labels and accumulates into loss4 / status before it waits for
+ * that kernel, which is safe only because its predecessor is this library's own kernel; behind anything else (the
+ * producer of raw or labels, the fill that zeroes loss4) use yl_loss_forward, a normal, fully ordered launch. */
+int yl_loss_forward_chained(const float *raw, const float *labels, int B, int F, int K, int C, int layer_no,
                     const float *anchors_px, const int *anchor_mask3, float ignore_thre,
                     double *loss4, float *gobj, int *tcell_all, int *mcell, float *mgrad, int *status,
                     yl_stream_t stream);

@@ -8,6 +8,7 @@ hp = yb.HeadPostprocessor(B, [76, 38, 19], 80, 1e-4, 0.4, cap_seg=int(os.environ
 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 for _ in range(20): hp.replay()
 torch.cuda.synchronize(); ev0.record()
-for _ in range(300): hp.replay()
+N = int(os.environ.get('N', '300'))
+for _ in range(N): hp.replay()
 ev1.record(); torch.cuda.synchronize()
-print(os.environ.get("TAG", ""), "%.2f us/step" % (ev0.elapsed_time(ev1) * 1e3 / 300))
+print(os.environ.get("TAG", ""), "%.2f us/step" % (ev0.elapsed_time(ev1) * 1e3 / N))

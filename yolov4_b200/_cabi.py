@@ -25,11 +25,24 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    path = os.environ.get("YL_LIB", _build.LIB)      # YL_LIB: load a tuning build instead of the default library
-    if not os.path.exists(path):
-        # build from source if a toolchain is present; otherwise fail loudly (never fall back to eager PyTorch)
-        path = _build.build_lib()
+    path = os.environ.get("YL_LIB")                  # YL_LIB: load a tuning build instead of the default library
+    if path is None:
+        # (re)build from source when the library is missing or older than csrc/ / include/ and a toolchain is present (a
+        # stale .so must never be loaded silently); without a toolchain an existing library is used, a missing one raises.
+        # There is no fall back to eager PyTorch.
+        path = _build.LIB
+        if _build.is_stale():
+            try:
+                path = _build.build_lib()
+            except Exception:
+                if not os.path.exists(path):
+                    raise
     L = ctypes.CDLL(path)
+    L.yl_source_hash.restype = ctypes.c_char_p
+    L.yl_source_hash.argtypes = []
+    if "YL_LIB" not in os.environ and L.yl_source_hash().decode() != _build.source_hash():
+        raise YoloHeadError("libyolohead.so was built from other sources than csrc/ and include/ hold now, and it could "
+                            "not be rebuilt (no nvcc?)")
     L.yl_abi_version.restype = _i
     L.yl_abi_version.argtypes = []
     L.yl_error_string.restype = ctypes.c_char_p
@@ -42,6 +55,8 @@ def lib():
     L.yl_decode_train.argtypes = [_p, _i, _i, _i, _p, _p, _p, _p]
     L.yl_decode_train_backward.restype = _i
     L.yl_decode_train_backward.argtypes = [_p, _p, _i, _i, _i, _p, _p]
+    L.yl_decode_train_backward_raw.restype = _i
+    L.yl_decode_train_backward_raw.argtypes = [_p, _p, _i, _i, _i, _p, _p]
     L.yl_post_workspace_bytes.restype = _sz
     L.yl_post_workspace_bytes.argtypes = [_i, _l, _i, _i]
     L.yl_post_reset.restype = _i
@@ -60,6 +75,8 @@ def lib():
     L.yl_coco_rows.argtypes = [_p, _p, _l, _p, _p, _p, _i, _i, _p, _p]
     L.yl_loss_forward.restype = _i
     L.yl_loss_forward.argtypes = [_p, _p, _i, _i, _i, _i, _i, _p, _p, _f, _p, _p, _p, _p, _p, _p, _p]
+    L.yl_loss_forward_chained.restype = _i
+    L.yl_loss_forward_chained.argtypes = L.yl_loss_forward.argtypes
     L.yl_loss_backward.restype = _i
     L.yl_loss_backward.argtypes = [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p]
     L.yl_context_create.restype = _i
@@ -75,9 +92,9 @@ def lib():
 
 
 EXPORTS = [
-    "yl_abi_version", "yl_error_string", "yl_selftest_rcp", "yl_decode_dense", "yl_decode_train", "yl_decode_train_backward",
+    "yl_abi_version", "yl_source_hash", "yl_error_string", "yl_selftest_rcp", "yl_decode_dense", "yl_decode_train", "yl_decode_train_backward", "yl_decode_train_backward_raw",
     "yl_post_workspace_bytes", "yl_post_reset", "yl_filter_raw", "yl_filter_raw_stage", "yl_filter_dense", "yl_nms", "yl_build_target", "yl_coco_rows",
-    "yl_loss_forward", "yl_loss_backward",
+    "yl_loss_forward", "yl_loss_forward_chained", "yl_loss_backward",
     "yl_context_create", "yl_context_destroy", "yl_detect_host",
 ]
 

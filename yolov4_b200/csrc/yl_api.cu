@@ -8,6 +8,11 @@
 
 extern "C" int yl_abi_version(void) { return YL_ABI_VERSION; }
 
+#ifndef YL_SOURCE_HASH
+#define YL_SOURCE_HASH "unknown"
+#endif
+extern "C" const char *yl_source_hash(void) { return YL_SOURCE_HASH; }
+
 extern "C" const char *yl_error_string(int code)
 {
     static thread_local char buf[160];

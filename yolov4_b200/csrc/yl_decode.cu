@@ -150,22 +150,38 @@ k_decode_train(const float *__restrict__ raw, int Fw, int F2, int C,
     }
 }
 
-template <int VEC>
+// FROM_RAW: `src` is the raw head tensor and sigmoid(raw) is recomputed with the spec sequence (the bits of the forward pass),
+// so the autograd node does not have to keep the tensor it returned: the reference's YOLOLoss.forward multiplies `output` by its
+// masks IN PLACE (yololoss.py:402-408), which would invalidate a saved `output`.  Otherwise `src` is the forward's output_planar.
+template <int VEC, bool FROM_RAW>
 __global__ void __launch_bounds__(DT_THREADS)
-k_decode_train_bwd(const float *__restrict__ output_planar, const float *__restrict__ grad_out, int F2, int C,
+k_decode_train_bwd(const float *__restrict__ src, const float *__restrict__ grad_out, int F2, int C,
                    float *__restrict__ grad_raw)
 {
     const int nch = 5 + C;
     const unsigned plane = blockIdx.x;
     const int k = (int)(plane % (unsigned)nch);
     const size_t base = (size_t)plane * F2;
+    const bool sig = (k != 2 && k != 3);
     for (int p = threadIdx.x * VEC; p < F2; p += DT_THREADS * VEC) {
         Vec<VEC> g, o;
         g.load(grad_out + base + p);
-        o.load(output_planar + base + p);
+        if (sig) {
+            o.load(src + base + p);
+            if (FROM_RAW) {
+                if (VEC == 4) {
+                    const float tt[4] = {o.v[0], o.v[1 % VEC], o.v[2 % VEC], o.v[3 % VEC]};
+                    float ss[4];
+                    spec_sigmoid_batch<4>(tt, ss);
+                    o.v[0] = ss[0]; o.v[1 % VEC] = ss[1]; o.v[2 % VEC] = ss[2]; o.v[3 % VEC] = ss[3];
+                } else {
+                    o.v[0] = spec_sigmoidf(o.v[0]);
+                }
+            }
+        }
         float r[VEC];
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) r[v] = (k == 2 || k == 3) ? g.v[v] : (g.v[v] * (1.0f - o.v[v])) * o.v[v];     // ATen sigmoid_backward order
+        for (int v = 0; v < VEC; ++v) r[v] = sig ? (g.v[v] * (1.0f - o.v[v])) * o.v[v] : g.v[v];     // ATen sigmoid_backward order
         if (VEC == 4) *reinterpret_cast<float4 *>(grad_raw + base + p) = make_float4(r[0], r[1 % VEC], r[2 % VEC], r[3 % VEC]);
         else grad_raw[base + p] = r[0];
     }
@@ -212,16 +228,34 @@ extern "C" int yl_decode_train(const float *raw, int B, int F, int C, const floa
     return YL_OK;
 }
 
-extern "C" int yl_decode_train_backward(const float *output_planar, const float *grad_out_planar, int B, int F, int C,
-                                        float *grad_raw, yl_stream_t stream)
+static int decode_train_backward_impl(const float *src, const float *grad_out_planar, int B, int F, int C, float *grad_raw,
+                                      yl_stream_t stream, bool from_raw)
 {
-    if (!output_planar || !grad_out_planar || !grad_raw || B <= 0 || F <= 0 || C <= 0) return YL_ERR_ARG;
+    if (!src || !grad_out_planar || !grad_raw || B <= 0 || F <= 0 || C <= 0) return YL_ERR_ARG;
     const int F2 = F * F;
     const long planes = (long)B * 3 * (5 + C);
     if (planes > 0x7FFFFFFFL) return YL_ERR_ARG;
-    const bool vec4 = (F2 % 4 == 0) && (((uintptr_t)output_planar | (uintptr_t)grad_out_planar | (uintptr_t)grad_raw) % 16 == 0);
-    if (vec4) k_decode_train_bwd<4><<<(unsigned)planes, DT_THREADS, 0, (cudaStream_t)stream>>>(output_planar, grad_out_planar, F2, C, grad_raw);
-    else k_decode_train_bwd<1><<<(unsigned)planes, DT_THREADS, 0, (cudaStream_t)stream>>>(output_planar, grad_out_planar, F2, C, grad_raw);
+    const bool vec4 = (F2 % 4 == 0) && (((uintptr_t)src | (uintptr_t)grad_out_planar | (uintptr_t)grad_raw) % 16 == 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (vec4) {
+        if (from_raw) k_decode_train_bwd<4, true><<<(unsigned)planes, DT_THREADS, 0, st>>>(src, grad_out_planar, F2, C, grad_raw);
+        else k_decode_train_bwd<4, false><<<(unsigned)planes, DT_THREADS, 0, st>>>(src, grad_out_planar, F2, C, grad_raw);
+    } else {
+        if (from_raw) k_decode_train_bwd<1, true><<<(unsigned)planes, DT_THREADS, 0, st>>>(src, grad_out_planar, F2, C, grad_raw);
+        else k_decode_train_bwd<1, false><<<(unsigned)planes, DT_THREADS, 0, st>>>(src, grad_out_planar, F2, C, grad_raw);
+    }
     YL_LAUNCH_CHECK();
     return YL_OK;
+}
+
+extern "C" int yl_decode_train_backward(const float *output_planar, const float *grad_out_planar, int B, int F, int C,
+                                        float *grad_raw, yl_stream_t stream)
+{
+    return decode_train_backward_impl(output_planar, grad_out_planar, B, F, C, grad_raw, stream, false);
+}
+
+extern "C" int yl_decode_train_backward_raw(const float *raw, const float *grad_out_planar, int B, int F, int C,
+                                            float *grad_raw, yl_stream_t stream)
+{
+    return decode_train_backward_impl(raw, grad_out_planar, B, F, C, grad_raw, stream, true);
 }

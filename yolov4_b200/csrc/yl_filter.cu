@@ -756,6 +756,313 @@ k_filter_raw_tma(const __grid_constant__ RawParams P, const __grid_constant__ Tm
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Warp-specialised form (default where the big scales are TMA-capable): ONE persistent kernel, one CTA per SM, three
+// kinds of warps that never wait for each other's memory latency:
+//   * streaming warps   private TMA rings ([WT_KC class planes x 128 boxes] per stage, UTMALDG.2D + transaction
+//                       mbarriers) exactly as above, but a finished tile (flag words + sigmoid(objectness), 2 KB) is
+//                       handed over through a shared-memory packet instead of being resolved in place, so the ring never
+//                       drains while a warp follows the dependent round trips of the exact pass;
+//   * emit warps        WS_EPS per streaming warp: wait for a packet, run the exact pass (emit_pairs: flagged logits and
+//                       box planes come back from L2 microseconds after the ring streamed them, slot atomics, 32-byte
+//                       records), give the packet back;
+//   * scalar warps      the scales whose planes are not 16-byte aligned (19x19: 4.8 % of the bytes) with register-staged
+//                       loads, stream + emit in the same warp, from their own tile counter.
+// No flag table or objectness table goes through global memory and there is no separate emit launch.
+// ---------------------------------------------------------------------------------------------------------------
+#ifndef YL_WS_STREAM
+#define YL_WS_STREAM 4
+#endif
+#ifndef YL_WS_EPS
+#define YL_WS_EPS 2
+#endif
+#ifndef YL_WS_STAGES
+#define YL_WS_STAGES 4
+#endif
+#ifndef YL_WS_SCALAR
+#define YL_WS_SCALAR 4
+#endif
+#ifndef YL_WS_MINB
+#define YL_WS_MINB 2                           // register cap = 65536 / (WS_THREADS * YL_WS_MINB): leaves room for co-resident NMS CTAs
+#endif
+constexpr int WS_STREAM = YL_WS_STREAM;        // streaming warps per CTA
+constexpr int WS_EPS = YL_WS_EPS;              // emit warps (= packets) per streaming warp
+constexpr int WS_STAGES = YL_WS_STAGES;        // ring stages per streaming warp (4 KB each)
+constexpr int WS_SCALAR = YL_WS_SCALAR;        // scalar warps per CTA
+constexpr int WS_EMIT = WS_STREAM * WS_EPS;
+constexpr int WS_THREADS = 32 * (WS_STREAM + WS_EMIT + WS_SCALAR);
+
+template <int NW>
+struct alignas(16) WsPacket {
+    unsigned bits[NW][WT_BOX];                 // flagged-class words per box slot of the tile
+    float sobj[WT_BOX];                        // sigmoid(objectness) per box slot
+    int layer, ba, p0, vec;                    // vec = 0: no more tiles
+};
+struct alignas(128) WsStream {
+    float stage[WS_STAGES][WT_KC][WT_BOX];
+    float objp[2][WT_BOX];                     // objectness plane of the current / the next tile
+    unsigned long long full[WS_STAGES], obj_full[2];
+};
+template <int NW>
+struct WsSmem {
+    WsStream s[WS_STREAM];
+    WsPacket<NW> pk[WS_EMIT];
+    EmitWarp em[WS_EMIT + WS_SCALAR];
+    float sobj_sc[WS_SCALAR > 0 ? WS_SCALAR : 1][32];
+    unsigned long long pk_full[WS_EMIT], pk_empty[WS_EMIT];
+};
+
+#ifndef YL_WS_SLEEP
+#define YL_WS_SLEEP 200
+#endif
+// Wait of a warp that has nothing else to do (emit warps between packets): back off between polls so that the spinning
+// does not take issue slots from the streaming warps of the same scheduler.
+__device__ __forceinline__ void mbar_wait_idle(unsigned long long *bar, unsigned parity)
+{
+    unsigned ok;
+    for (;;) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (ok) break;
+        if (YL_WS_SLEEP > 0) __nanosleep(YL_WS_SLEEP);
+    }
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// t-th tile among the scales with layer.tma == tma (P.layer[] of this form holds every scale; layer[l].tiles = warp
+// tiles per (image, anchor)); np == 0: no such tile.
+__device__ __forceinline__ WtTile ws_tile(const RawParams &P, int t, int nba, int tma)
+{
+    WtTile T;
+    T.np = 0; T.src = nullptr; T.layer = 0; T.ba = 0; T.p0 = 0; T.row0 = 0; T.tma = tma;
+    for (int l = 0; l < P.n_layers; ++l) {
+        if (P.layer[l].tma != tma) continue;
+        const int tp = P.layer[l].tiles, cnt = tp * nba;
+        if (t < cnt) {
+            const int bal = t / tp, tx = t - bal * tp;
+            T.layer = l;
+            T.ba = P.img_first * 3 + bal;
+            T.p0 = tx * P.layer[l].tile_boxes;
+            T.np = min(P.layer[l].tile_boxes, P.layer[l].F2 - T.p0);
+            T.src = P.layer[l].raw + ((size_t)T.ba * (5 + P.C)) * P.layer[l].F2 + T.p0;
+            T.row0 = T.ba * (5 + P.C) + 5;
+            return T;
+        }
+        t -= cnt;
+    }
+    return T;
+}
+
+// Streaming warp -> emit warp: packet e = warp * WS_EPS + (n_sent mod WS_EPS); a tile without a flagged pair sends nothing.
+template <int NW>
+__device__ __forceinline__ void ws_send(WsSmem<NW> &S, int warp, unsigned &n_sent, int layer, int ba, int p0,
+                                        const float (&obj)[4], const unsigned (&bits)[4][NW])
+{
+    const int lane = threadIdx.x & 31;
+    unsigned any = 0u;
+#pragma unroll
+    for (int v = 0; v < 4; ++v)
+#pragma unroll
+        for (int w = 0; w < NW; ++w) any |= bits[v][w];
+    if (!__any_sync(0xFFFFFFFFu, any != 0u)) return;
+    const int e = warp * WS_EPS + (int)(n_sent % WS_EPS);
+    mbar_wait(&S.pk_empty[e], ((n_sent / WS_EPS) & 1u) ^ 1u);       // first use: passes on the fresh barrier
+    WsPacket<NW> &K = S.pk[e];
+    *reinterpret_cast<float4 *>(&K.sobj[lane * 4]) = make_float4(obj[0], obj[1], obj[2], obj[3]);
+#pragma unroll
+    for (int w = 0; w < NW; ++w)
+        *reinterpret_cast<uint4 *>(&K.bits[w][lane * 4]) = make_uint4(bits[0][w], bits[1][w], bits[2][w], bits[3][w]);
+    if (lane == 0) { K.layer = layer; K.ba = ba; K.p0 = p0; K.vec = 4; }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&S.pk_full[e]);
+    ++n_sent;
+}
+
+template <int NW>
+__global__ void __launch_bounds__(WS_THREADS, YL_WS_MINB)
+k_filter_raw_ws(const __grid_constant__ RawParams P, const __grid_constant__ TmaMaps maps, int nba,
+                unsigned *__restrict__ tile_counter, unsigned *__restrict__ scalar_counter)
+{
+    extern __shared__ __align__(128) unsigned char ws_smem_raw[];
+    WsSmem<NW> &S = *reinterpret_cast<WsSmem<NW> *>(ws_smem_raw);
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int C = P.C;
+
+    if (threadIdx.x == 0) {
+        for (int w = 0; w < WS_STREAM; ++w) {
+            for (int s = 0; s < WS_STAGES; ++s) mbar_init(&S.s[w].full[s], 1);
+            mbar_init(&S.s[w].obj_full[0], 1);
+            mbar_init(&S.s[w].obj_full[1], 1);
+        }
+        for (int e = 0; e < WS_EMIT; ++e) { mbar_init(&S.pk_full[e], 1); mbar_init(&S.pk_empty[e], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    pdl_trigger();
+
+    if (warp < WS_STREAM) {
+        // ---------------- streaming warp ----------------
+        WsStream &W = S.s[warp];
+        const int n_cc = (C + WT_KC - 1) / WT_KC;                    // class chunks per tile (>= WS_STAGES, host-checked)
+        unsigned n_sent = 0u;
+        auto issue_chunk = [&](const WtTile &T, int c, int s) {
+            mbar_expect_tx(&W.full[s], WT_KC * WT_BOX * 4u);         // full box, zero fill included
+            tma_load_2d(&W.stage[s][0][0], &maps.m[T.layer], T.p0, T.row0 + c * WT_KC, &W.full[s]);
+        };
+        auto issue_obj = [&](const WtTile &T, int slot) {
+            const unsigned bytes = (unsigned)T.np * 4u;
+            mbar_expect_tx(&W.obj_full[slot], bytes);
+            bulk_g2s(&W.objp[slot][0], T.src + 4 * (size_t)P.layer[T.layer].F2, bytes, &W.obj_full[slot]);
+        };
+        // the tile counter's round trip is taken one tile ahead: `ahead` is the ticket of the tile after `nxt`, drawn at
+        // the top of an iteration and first used at its bottom
+#ifdef YL_WS_STATIC                                                       // (diagnostic build: round-robin tiles, no counter)
+        int static_next = blockIdx.x * WS_STREAM + warp;
+        auto draw = [&]() { const int t = static_next; static_next += gridDim.x * WS_STREAM; return t; };
+#else
+        auto draw = [&]() { int t = 0; if (lane == 0) t = (int)atomicAdd(tile_counter, 1u); return t; };
+#endif
+        auto resolve = [&](int t) { return ws_tile(P, __shfl_sync(FULL, t, 0), nba, 1); };
+        WtTile cur = resolve(draw());
+        WtTile nxt = cur;
+        if (cur.np != 0) nxt = resolve(draw());
+        if (lane == 0 && cur.np != 0) {
+            issue_obj(cur, 0);
+            for (int c = 0; c < WS_STAGES; ++c) issue_chunk(cur, c, c);
+        }
+        int s = 0;                       // ring stage of the next chunk to consume
+        unsigned ph = 0u;                // phase bit per ring stage
+        unsigned it = 0u;                // tiles processed (objectness slot = it & 1, its phase = (it >> 1) & 1)
+        while (cur.np != 0) {
+            const int ahead = (nxt.np != 0) ? draw() : 0;
+            if (lane == 0 && nxt.np != 0) issue_obj(nxt, (it + 1) & 1);
+            const bool inb = lane * 4 < cur.np;
+            float obj[4], lth[4];
+            {
+                mbar_wait(&W.obj_full[it & 1], (it >> 1) & 1u);
+                const float4 to = *reinterpret_cast<const float4 *>(&W.objp[it & 1][lane * 4]);
+                const float tv[4] = {to.x, to.y, to.z, to.w};
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    obj[v] = inb ? spec_sigmoidf(tv[v]) : 0.0f;
+                    lth[v] = inb ? class_logit_bound(obj[v], P.thr) : kInf;
+                }
+            }
+            unsigned bits[4][NW];
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                unsigned m0 = 0u, m1 = 0u, m2 = 0u, m3 = 0u;
+#pragma unroll 1
+                for (int cc = 0; cc < 32 / WT_KC; ++cc) {
+                    const int c = w * (32 / WT_KC) + cc;                 // class chunk index
+                    if (c >= n_cc) break;                                // warp-uniform
+                    mbar_wait(&W.full[s], (ph >> s) & 1u);
+                    const int kn = min(WT_KC, C - c * WT_KC);
+                    const float *sp = &W.stage[s][0][lane * 4];
+                    unsigned a0 = 0u, a1 = 0u, a2 = 0u, a3 = 0u;
+#ifndef YL_WS_NOCOMPARE                                                  // (diagnostic build: the TMA ring alone)
+                    if (kn == WT_KC) {
+                        // full chunk (every chunk when C is a multiple of WT_KC): all LDS.128 issued before the first compare
+                        float4 tv[WT_KC];
+#pragma unroll
+                        for (int k = 0; k < WT_KC; ++k) tv[k] = *reinterpret_cast<const float4 *>(sp + k * WT_BOX);
+#pragma unroll
+                        for (int k = 0; k < WT_KC; ++k) {
+                            flag_or(a0, tv[k].x, lth[0], 1u << k);
+                            flag_or(a1, tv[k].y, lth[1], 1u << k);
+                            flag_or(a2, tv[k].z, lth[2], 1u << k);
+                            flag_or(a3, tv[k].w, lth[3], 1u << k);
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < WT_KC; ++k)
+                            if (k < kn) {
+                                const float4 tv = *reinterpret_cast<const float4 *>(sp + k * WT_BOX);
+                                flag_or(a0, tv.x, lth[0], 1u << k);
+                                flag_or(a1, tv.y, lth[1], 1u << k);
+                                flag_or(a2, tv.z, lth[2], 1u << k);
+                                flag_or(a3, tv.w, lth[3], 1u << k);
+                            }
+                    }
+#endif
+                    const int sh = cc * WT_KC;
+                    m0 |= a0 << sh; m1 |= a1 << sh; m2 |= a2 << sh; m3 |= a3 << sh;
+                    __syncwarp();                                        // every lane has read the stage
+                    if (lane == 0) {
+                        const int cn = c + WS_STAGES;                    // the chunk that takes this stage next
+                        if (cn < n_cc) issue_chunk(cur, cn, s);
+                        else if (nxt.np != 0) issue_chunk(nxt, cn - n_cc, s);
+                    }
+                    ph ^= 1u << s;
+                    s = (s + 1 == WS_STAGES) ? 0 : s + 1;
+                }
+                // a dead box (objectness below the threshold, or outside the tile) flags nothing, whatever its logits are
+                bits[0][w] = (lth[0] == kInf) ? 0u : m0; bits[1][w] = (lth[1] == kInf) ? 0u : m1;
+                bits[2][w] = (lth[2] == kInf) ? 0u : m2; bits[3][w] = (lth[3] == kInf) ? 0u : m3;
+            }
+            ws_send<NW>(S, warp, n_sent, cur.layer, cur.ba, cur.p0, obj, bits);
+            cur = nxt;
+            if (nxt.np != 0) nxt = resolve(ahead);
+            ++it;
+        }
+        for (int k = 0; k < WS_EPS; ++k) {                              // tell this warp's emit warps to stop
+            const int e = warp * WS_EPS + (int)(n_sent % WS_EPS);
+            mbar_wait(&S.pk_empty[e], ((n_sent / WS_EPS) & 1u) ^ 1u);
+            if (lane == 0) S.pk[e].vec = 0;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S.pk_full[e]);
+            ++n_sent;
+        }
+    } else if (warp < WS_STREAM + WS_EMIT) {
+        // ---------------- emit warp ----------------
+        const int e = warp - WS_STREAM;
+        WsPacket<NW> &K = S.pk[e];
+        EmitWarp &E = S.em[e];
+        for (unsigned n = 0u;; ++n) {
+            mbar_wait_idle(&S.pk_full[e], n & 1u);
+            if (K.vec == 0) break;                                       // warp-uniform
+#ifdef YL_WS_NOEMIT                                                      // diagnostic build: the streaming side alone
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S.pk_empty[e]);
+            continue;
+#endif
+            float lth[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            unsigned bits[4][NW];
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                const uint4 m = *reinterpret_cast<const uint4 *>(&K.bits[w][lane * 4]);
+                bits[0][w] = m.x; bits[1][w] = m.y; bits[2][w] = m.z; bits[3][w] = m.w;
+            }
+            emit_pairs<4, NW>(P, P.layer[K.layer], K.ba, K.p0, lth, bits, E, K.sobj);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S.pk_empty[e]);
+        }
+    } else {
+        // ---------------- scalar warp ----------------
+        const int k = warp - WS_STREAM - WS_EMIT;
+        EmitWarp &E = S.em[WS_EMIT + k];
+        float *sobj1 = S.sobj_sc[k];
+        for (;;) {
+            int t = 0;
+            if (lane == 0) t = (int)atomicAdd(scalar_counter, 1u);
+            const WtTile T = ws_tile(P, __shfl_sync(FULL, t, 0), nba, 0);
+            if (T.np == 0) break;
+            const RawLayer &Ly = P.layer[T.layer];
+            float obj1[1], lth1[1];
+            unsigned bits1[1][NW];
+            ldg_stream<1, NW>(P, Ly, T.ba, T.p0 + lane, lane < T.np, obj1, lth1, bits1);
+            __syncwarp();
+            sobj1[lane] = obj1[0];
+            emit_pairs<1, NW>(P, Ly, T.ba, T.p0, lth1, bits1, E, sobj1);
+            __syncwarp();
+        }
+    }
+}
+
 // grid = (sum of tiles over the scales, img_count*3): one launch covers all scales of an image group.
 template <int NW>
 __global__ void __launch_bounds__(K1_THREADS)
@@ -965,7 +1272,9 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32
 static const bool g_use_tma = !(getenv("YL_NO_TMA") && getenv("YL_NO_TMA")[0] == '1');
 // YL_FILTER selects the front-end form: "split" (default: lean streaming flag kernel + emit kernel),
 // "fused" (one kernel streams and emits: the TMA pipeline where planes are 16-byte aligned, register-staged otherwise).
-static const bool g_split = !(getenv("YL_FILTER") && strcmp(getenv("YL_FILTER"), "fused") == 0);
+// "ws" (warp-specialised persistent kernel: TMA streaming warps + emit warps, no flag table, no emit launch).
+static const bool g_ws = getenv("YL_FILTER") && strcmp(getenv("YL_FILTER"), "ws") == 0;
+static const bool g_split = !g_ws && !(getenv("YL_FILTER") && strcmp(getenv("YL_FILTER"), "fused") == 0);
 // YL_FLAG_SMEM=<bytes, at most 48 KB>: dynamic shared memory requested (and not used) by k_flag_raw, which caps its CTAs per
 // SM so that CTAs of other kernels can be co-resident (cross-step pipelining experiments, tools/xstep_probe.py).
 static const int g_flag_smem = getenv("YL_FLAG_SMEM") ? atoi(getenv("YL_FLAG_SMEM")) : 0;
@@ -1055,7 +1364,7 @@ static int filter_raw_impl(const float *const *raw, const int *F, int n_layers, 
         }
         // 128-bit loads / bulk copies need 16-byte aligned planes: F^2 % 4 == 0 and an aligned base (19x19, 13x13 fall back)
         Ly.vec = ((Ly.F2 % 4 == 0) && (((uintptr_t)raw[l]) % 16 == 0)) ? 4 : 1;
-        Ly.tma = (Ly.vec == 4 && g_use_tma && (C + WT_KC - 1) / WT_KC >= WT_STAGES) ? 1 : 0;
+        Ly.tma = (Ly.vec == 4 && g_use_tma && (C + WT_KC - 1) / WT_KC >= (g_ws ? WS_STAGES : WT_STAGES)) ? 1 : 0;
         n_tma += Ly.tma;
         row_off += 3 * Ly.F2;
     }
@@ -1090,6 +1399,7 @@ static int filter_raw_impl(const float *const *raw, const int *F, int n_layers, 
         const int want = (n_tiles + K1_WARPS - 1) / K1_WARPS;
         const int grid = want < ctas_per_sm * g_num_sms() ? want : ctas_per_sm * g_num_sms();
         unsigned *tile_counter = (unsigned *)(w + L.off_tile_count) + img_first;
+        unsigned *scalar_counter = (unsigned *)(w + L.off_tile_count) + B + img_first;
         TmaMaps maps;
         memset(&maps, 0, sizeof(maps));
         for (int l = 0; l < Pt.n_layers; ++l) {
@@ -1106,7 +1416,21 @@ static int filter_raw_impl(const float *const *raw, const int *F, int n_layers, 
         }                                                                                                            \
         k_filter_raw_tma<NW_><<<grid, K1_THREADS, smem, st>>>(Pt, maps, nba, n_tiles, tile_counter);                       \
     } break;
-        switch (NW) { YL_TMA_CASE(1) YL_TMA_CASE(2) YL_TMA_CASE(3) YL_TMA_CASE(4) }
+#define YL_WS_CASE(NW_)                                                                                              \
+    case NW_: {                                                                                                      \
+        static bool attr_done = false;                                                                               \
+        const size_t smem_ws = sizeof(WsSmem<NW_>);                                                                  \
+        if (!attr_done) {                                                                                            \
+            YL_CUDA_TRY(cudaFuncSetAttribute(k_filter_raw_ws<NW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ws)); \
+            attr_done = true;                                                                                        \
+        }                                                                                                            \
+        const int want_ws = (n_tiles + WS_STREAM - 1) / WS_STREAM;                                                   \
+        const int grid_ws = want_ws < g_num_sms() ? want_ws : g_num_sms();                                           \
+        k_filter_raw_ws<NW_><<<grid_ws, WS_THREADS, smem_ws, st>>>(Pt, maps, nba, tile_counter, scalar_counter);      \
+    } break;
+        if (g_ws) { switch (NW) { YL_WS_CASE(1) YL_WS_CASE(2) YL_WS_CASE(3) YL_WS_CASE(4) } }
+        else switch (NW) { YL_TMA_CASE(1) YL_TMA_CASE(2) YL_TMA_CASE(3) YL_TMA_CASE(4) }
+#undef YL_WS_CASE
 #undef YL_TMA_CASE
         YL_LAUNCH_CHECK();
     }

@@ -260,10 +260,10 @@ static int fill_anchors(LossAnchors &A, const float *anchors_px, const int *anch
 
 using namespace yl;
 
-extern "C" int yl_loss_forward(const float *raw, const float *labels, int B, int F, int K, int C, int layer_no,
-                               const float *anchors_px, const int *anchor_mask3, float ignore_thre,
-                               double *loss4, float *gobj, int *tcell_all, int *mcell, float *mgrad, int *status,
-                               yl_stream_t stream)
+static int loss_forward_impl(const float *raw, const float *labels, int B, int F, int K, int C, int layer_no,
+                             const float *anchors_px, const int *anchor_mask3, float ignore_thre,
+                             double *loss4, float *gobj, int *tcell_all, int *mcell, float *mgrad, int *status,
+                             int chained, yl_stream_t stream)
 {
     if (!raw || !labels || !anchors_px || !anchor_mask3 || !loss4 || !gobj || !tcell_all || !mcell || !mgrad) return YL_ERR_ARG;
     if (B <= 0 || F <= 0 || K <= 0 || K > TG_MAXK || C <= 0 || layer_no < 0 || layer_no > 2) return YL_ERR_ARG;
@@ -273,14 +273,35 @@ extern "C" int yl_loss_forward(const float *raw, const float *labels, int B, int
     const int rc = fill_anchors(A, anchors_px, anchor_mask3, stride);
     if (rc != YL_OK) return rc;
     // programmatic dependent launch along match(l) -> obj(l) -> match(l+1) -> ...: the latency-bound match kernels and the
-    // small scales' obj kernels fill the tails of their neighbours (see the waits in the kernels)
+    // small scales' obj kernels fill the tails of their neighbours (see the waits in the kernels).  k_loss_match reads raw /
+    // labels and adds into loss4 / status BEFORE it waits, so it may only be launched programmatically behind this library's
+    // own k_loss_obj (chained != 0): behind a foreign kernel (the producer of raw or labels, the fill of loss4) it is a
+    // normal launch, fully ordered after everything earlier on the stream.
     const bool pdl = pdl_enabled();
-    YL_CUDA_TRY(launch_after(k_loss_match, dim3(B, 8), dim3(LS_THREADS), 0, st, pdl, raw, labels, F, K, C, stride, A, loss4, tcell_all,
-                             mcell, mgrad, status));
+    YL_CUDA_TRY(launch_after(k_loss_match, dim3(B, 8), dim3(LS_THREADS), 0, st, pdl && chained != 0, raw, labels, F, K, C, stride, A,
+                             loss4, tcell_all, mcell, mgrad, status));
     dim3 grid((3 * F * F + LS_THREADS - 1) / LS_THREADS, B);
     YL_CUDA_TRY(launch_after(k_loss_obj, grid, dim3(LS_THREADS), 0, st, pdl, raw, labels, F, K, C, stride, A, ignore_thre,
                              (const int *)tcell_all, loss4, gobj));
     return YL_OK;
+}
+
+extern "C" int yl_loss_forward(const float *raw, const float *labels, int B, int F, int K, int C, int layer_no,
+                               const float *anchors_px, const int *anchor_mask3, float ignore_thre,
+                               double *loss4, float *gobj, int *tcell_all, int *mcell, float *mgrad, int *status,
+                               yl_stream_t stream)
+{
+    return loss_forward_impl(raw, labels, B, F, K, C, layer_no, anchors_px, anchor_mask3, ignore_thre, loss4, gobj, tcell_all,
+                             mcell, mgrad, status, 0, stream);
+}
+
+extern "C" int yl_loss_forward_chained(const float *raw, const float *labels, int B, int F, int K, int C, int layer_no,
+                                       const float *anchors_px, const int *anchor_mask3, float ignore_thre,
+                                       double *loss4, float *gobj, int *tcell_all, int *mcell, float *mgrad, int *status,
+                                       yl_stream_t stream)
+{
+    return loss_forward_impl(raw, labels, B, F, K, C, layer_no, anchors_px, anchor_mask3, ignore_thre, loss4, gobj, tcell_all,
+                             mcell, mgrad, status, 1, stream);
 }
 
 extern "C" int yl_loss_backward(const float *gobj, const int *mcell, const float *mgrad, const float *upstream,

@@ -2,10 +2,14 @@
 import importlib
 
 
-def patch_reference():
+def patch_reference(loss_forward=True):
     """Monkey-patches the three symbols of the drop-in boundary:
         yolo.model.yololayer.YOLOLayer, yolo.util.utils.postprocess, yolo.model.yololoss.YOLOLoss.build_target
-    and the names other reference modules imported from them.  Returns the list of patched attributes."""
+    and the names other reference modules imported from them.  With loss_forward=True (default) YOLOLoss.forward is
+    rebound as well (row A8: the same arithmetic written out of place, one pinned label upload for the three layers, row
+    N4); with False the reference's own forward keeps running on top of the B200 YOLOLayer and build_target -- it
+    multiplies dict['output'] by its masks in place (yololoss.py:402-408), which the autograd node of the B200 YOLOLayer
+    tolerates because it keeps the raw tensor, not its output.  Returns the list of patched attributes."""
     from . import yololayer as my_layer, postprocess as my_post, yololoss as my_loss
     done = []
     ref_layer = importlib.import_module("yolo.model.yololayer")
@@ -17,6 +21,9 @@ def patch_reference():
     ref_loss = importlib.import_module("yolo.model.yololoss")
     ref_loss.YOLOLoss.build_target = my_loss.YOLOLoss.build_target
     done.append("yolo.model.yololoss.YOLOLoss.build_target")
+    if loss_forward:
+        ref_loss.YOLOLoss.forward = my_loss.YOLOLoss.forward
+        done.append("yolo.model.yololoss.YOLOLoss.forward")
     for modname, attr, val in (("yolo.model.yolov4", "YOLOLayer", my_layer.YOLOLayer),
                                ("yolo.engine.build", "postprocess", my_post.postprocess)):
         try:

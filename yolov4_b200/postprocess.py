@@ -7,6 +7,8 @@
 
 All compute runs in libyolohead.so (hand-written sm_100a kernels) through the C ABI; there is no eager fallback.
 """
+import threading
+
 import numpy as np
 import torch
 
@@ -36,7 +38,8 @@ def _next_pow2(n):
 
 
 class _Workspace:
-    """Device scratch for one (device, B, M, C, cap_seg); reused across calls on the same stream."""
+    """Device scratch for one (device, stream, thread, B, M, C, cap_seg): calls of the same shape on different CUDA streams
+    or host threads may run concurrently and must not share candidate buffers and counters."""
 
     _cache = {}
 
@@ -49,11 +52,11 @@ class _Workspace:
 
     @classmethod
     def get(cls, device, B, M, C, cap_seg):
-        key = (str(device), B, M, C, cap_seg)
+        key = (str(device), int(torch.cuda.current_stream(device).cuda_stream), threading.get_ident(), B, M, C, cap_seg)
         ws = cls._cache.get(key)
         if ws is None:
-            # keep one workspace per (device, B, M, C): drop smaller-capacity predecessors
-            for k in [k for k in cls._cache if k[:4] == key[:4]]:
+            # keep one workspace per (device, stream, thread, B, M, C): drop smaller-capacity predecessors
+            for k in [k for k in cls._cache if k[:6] == key[:6]]:
                 del cls._cache[k]
             ws = cls._cache[key] = cls(device, B, M, C, cap_seg)
         return ws
@@ -138,8 +141,12 @@ def postprocess(prediction, num_classes, conf_thre=0.7, nms_thre=0.45):
 
 
 def _check_raws(head_outputs, num_classes):
+    # the library takes the scale of a head tensor from its position (stride 8 << l, anchor_mask[l]; yololayer.py:54,60):
+    # a caller with fewer heads passes them in the reference's order starting at the stride-8 head
     if len(head_outputs) < 1 or len(head_outputs) > 3:
-        raise ValueError("expected 1..3 head tensors")
+        raise ValueError("expected 1..3 head tensors (stride 8, 16, 32 in this order)")
+    if any(head_outputs[i].shape[2] < head_outputs[i + 1].shape[2] for i in range(len(head_outputs) - 1)):
+        raise ValueError("head tensors must be ordered stride 8, 16, 32 (largest grid first; yolov4.py:324)")
     B = head_outputs[0].shape[0]
     Fs = []
     raws = []
@@ -212,7 +219,11 @@ class HeadPostprocessor:
 
     def run(self, head_outputs):
         L, B, C, M = self.L, self.B, self.C, self.M
-        rp = _cabi.ptrs([r.data_ptr() for r in head_outputs])
+        raws, Bc, Fs = _check_raws(head_outputs, C)      # shape / dtype / device checked, non-contiguous inputs copied
+        if Bc != B or Fs != self.Fs:
+            raise ValueError("shape mismatch with the configured postprocessor")
+        self._live_inputs = raws                         # a contiguous copy must outlive the enqueued kernels
+        rp = _cabi.ptrs([r.data_ptr() for r in raws])
         main = torch.cuda.current_stream(self.device)
         G = self.n_groups
         fold_reset = (G == 1 and self.mode != "emit_side")    # one group: the flag kernel zeroes the counters itself

@@ -31,21 +31,25 @@ class _DecodeTrain(torch.autograd.Function):
         with torch.cuda.device(raw.device):
             _cabi.check(_cabi.lib().yl_decode_train(raw.data_ptr(), B, F, n_classes, anch, out.data_ptr(), pred.data_ptr(),
                                                     _stream()))
-        ctx.save_for_backward(out)
+        # The RAW tensor is what the backward pass keeps, not `out`: the reference's YOLOLoss.forward multiplies
+        # dict['output'] (a view of `out`) by its masks in place (yololoss.py:402-408), which would bump the version of a
+        # saved `out` and make loss.backward() raise.  The backward kernel recomputes sigmoid(raw) (same bits).
+        ctx.save_for_backward(raw)
         ctx.n_classes = n_classes
         ctx.mark_non_differentiable(pred)
         return out, pred
 
     @staticmethod
     def backward(ctx, grad_out, _grad_pred):
-        (out,) = ctx.saved_tensors
-        B, _, nch, F, _ = out.shape
+        (raw,) = ctx.saved_tensors
+        B, _, F, _ = raw.shape
+        nch = 5 + ctx.n_classes
         g = grad_out.contiguous()
-        grad_raw = torch.empty_like(out)
-        with torch.cuda.device(out.device):
-            _cabi.check(_cabi.lib().yl_decode_train_backward(out.data_ptr(), g.data_ptr(), B, F, ctx.n_classes,
-                                                             grad_raw.data_ptr(), _stream()))
-        return grad_raw.view(B, 3 * nch, F, F), None, None
+        grad_raw = torch.empty_like(raw)
+        with torch.cuda.device(raw.device):
+            _cabi.check(_cabi.lib().yl_decode_train_backward_raw(raw.data_ptr(), g.data_ptr(), B, F, ctx.n_classes,
+                                                                 grad_raw.data_ptr(), _stream()))
+        return grad_raw, None, None
 
 
 class YOLOLayer(nn.Module):

@@ -18,6 +18,39 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+class _LabelUploader:
+    """N4: the padded labels [B,K,5] of a step (float64 on the host as the loader collates them,
+    yolo/data/transform.py:464-471) are cast to fp32 once on the host, staged in pinned memory and uploaded with ONE
+    asynchronous copy that the three scales share -- the reference clones, uploads and casts them once per layer
+    (yololoss.py:392, :129).  One staging buffer per (shape, device); an event guards its reuse."""
+
+    _stage = {}
+
+    @classmethod
+    def upload(cls, labels, device):
+        device = torch.device(device)
+        if labels.is_cuda:
+            return labels.to(device=device, dtype=torch.float32).contiguous()
+        key = (tuple(labels.shape), str(device))
+        ent = cls._stage.get(key)
+        if ent is None:
+            ent = cls._stage[key] = [torch.empty(tuple(labels.shape), dtype=torch.float32).pin_memory(), None]
+        buf, ev = ent
+        if ev is not None:
+            ev.synchronize()                       # the previous step's copy out of this buffer has finished
+        buf.copy_(labels)                          # host cast float64 -> fp32 (the value yololoss.py:129 computes)
+        with torch.cuda.device(device):
+            dev = buf.to(device, non_blocking=True)
+            ent[1] = torch.cuda.Event()
+            ent[1].record()
+        return dev
+
+
+def upload_labels(labels, device):
+    """One pinned fp32 upload of the padded labels, to be shared by the three scales (row N4)."""
+    return _LabelUploader.upload(labels, device)
+
+
 def build_target(output, pred, layer_no, labels, anchors, anchor_mask, ignore_thresh, n_classes, strict=False):
     """Functional form.  output: only shape/dtype/device are used (as in the reference); pred [B,3,F,F,4] any strides;
     labels [B,K,5] (xc,yc,w,h,cls) in input pixels, zero padded, any float dtype (cast to fp32 like yololoss.py:129).
@@ -28,7 +61,7 @@ def build_target(output, pred, layer_no, labels, anchors, anchor_mask, ignore_th
     n_ch = 5 + n_classes
     assert output.shape[-1] == n_ch and A == 3
     dev = pred.device
-    lab = labels.to(device=dev, dtype=torch.float32).contiguous()
+    lab = upload_labels(labels, dev)
     K = int(lab.shape[1])
     target = torch.empty((B, 3, F, F, n_ch), dtype=torch.float32, device=dev)
     obj_mask = torch.empty((B, 3, F, F), dtype=torch.float32, device=dev)
@@ -72,11 +105,13 @@ class YOLOLoss(nn.Module):
     def forward(self, outputs, targets):
         assert isinstance(outputs, list) and isinstance(targets, dict)
         total = 0
+        labels = None
         for od in outputs:
             layer_no = od['layer_no']
             output = od['output'].to(self.device)
             pred = od['pred'].to(self.device)
-            labels = targets['padded_labels'].to(self.device)
+            if labels is None:
+                labels = upload_labels(targets['padded_labels'], pred.device)      # once for the three layers (N4)
             target, obj_mask, tgt_mask, tgt_scale = self.build_target(output, pred, layer_no, labels)
             n_ch = output.shape[-1]
             sel = np.r_[0:4, 5:n_ch]
@@ -104,14 +139,15 @@ class _FusedYoloLoss(torch.autograd.Function):
     def forward(ctx, labels, anchors, anchor_mask, ignore_thresh, n_classes, *raws):
         L = _cabi.lib()
         dev = raws[0].device
-        lab = labels.to(device=dev, dtype=torch.float32).contiguous()
+        lab = upload_labels(labels, dev)
         B, K = int(lab.shape[0]), int(lab.shape[1])
         C = int(n_classes)
-        loss4 = torch.zeros(4, dtype=torch.float64, device=dev)
-        status = torch.zeros(1, dtype=torch.int32, device=dev)
         anch = _cabi.floats([v for wh in anchors for v in wh])
         saved, keep = [], []
         with torch.cuda.device(dev):
+            loss4 = torch.zeros(4, dtype=torch.float64, device=dev)
+            status = torch.zeros(1, dtype=torch.int32, device=dev)
+            calls = []
             for l, r in enumerate(raws):
                 if not r.is_cuda or r.dtype != torch.float32 or r.dim() != 4 or r.shape[1] != 3 * (5 + C) or r.shape[0] != B:
                     raise TypeError("fused YOLO loss needs float32 CUDA head tensors [B, 3*(5+C), F, F]; there is no CPU fallback")
@@ -121,11 +157,16 @@ class _FusedYoloLoss(torch.autograd.Function):
                 tcell = torch.empty((B, K), dtype=torch.int32, device=dev)
                 mcell = torch.empty((B, K), dtype=torch.int32, device=dev)
                 mgrad = torch.empty((B, K, 4 + C), dtype=torch.float32, device=dev)
-                _cabi.check(L.yl_loss_forward(rc.data_ptr(), lab.data_ptr(), B, F, K, C, l, anch, _cabi.ints(anchor_mask[l]),
-                                              float(np.float32(ignore_thresh)), loss4.data_ptr(), gobj.data_ptr(), tcell.data_ptr(),
-                                              mcell.data_ptr(), mgrad.data_ptr(), status.data_ptr(), _stream()))
+                calls.append((rc, F, l, gobj, tcell, mcell, mgrad))
                 saved += [gobj, mcell, mgrad]
-                keep.append(tcell)          # see yl_loss_forward: the scales' kernels overlap, their buffers must not alias
+                keep += [rc, tcell]         # see yl_loss_forward: the scales' kernels overlap, their buffers must not alias
+            # every foreign kernel (contiguous copies, the fills of loss4 / status) is enqueued by now: the calls below are back
+            # to back on the stream, so the second and later ones may be launched programmatically behind their predecessor
+            for i, (rc, F, l, gobj, tcell, mcell, mgrad) in enumerate(calls):
+                fn = L.yl_loss_forward if i == 0 else L.yl_loss_forward_chained
+                _cabi.check(fn(rc.data_ptr(), lab.data_ptr(), B, F, K, C, l, anch, _cabi.ints(anchor_mask[l]),
+                               float(np.float32(ignore_thresh)), loss4.data_ptr(), gobj.data_ptr(), tcell.data_ptr(),
+                               mcell.data_ptr(), mgrad.data_ptr(), status.data_ptr(), _stream()))
         ctx.save_for_backward(*saved)
         ctx.shapes = [tuple(r.shape) for r in raws]
         ctx.K, ctx.C = K, C
@@ -163,14 +204,15 @@ def fused_yolo_loss_components(head_outputs, padded_labels, cfg, ignore_thresh=0
     tensor, no autograd.  `layers[i]` is the layer number of head_outputs[i] (default 0, 1, 2)."""
     L = _cabi.lib()
     dev = head_outputs[0].device
-    lab = padded_labels.to(device=dev, dtype=torch.float32).contiguous()
+    lab = upload_labels(padded_labels, dev)
     B, K = int(lab.shape[0]), int(lab.shape[1])
     C = int(cfg['N_CLASSES'])
-    loss4 = torch.zeros(4, dtype=torch.float64, device=dev)
     anch = _cabi.floats([v for wh in cfg['ANCHORS'] for v in wh])
     layers = list(range(len(head_outputs))) if layers is None else layers
     keep = []                   # the scales' kernels overlap on the device (yl_loss_forward): no buffer is reused between them
     with torch.cuda.device(dev):
+        loss4 = torch.zeros(4, dtype=torch.float64, device=dev)
+        calls = []
         for l, r in zip(layers, head_outputs):
             rc = r.detach().contiguous()
             F = int(rc.shape[2])
@@ -178,8 +220,11 @@ def fused_yolo_loss_components(head_outputs, padded_labels, cfg, ignore_thresh=0
             tcell = torch.empty((B, K), dtype=torch.int32, device=dev)
             mcell = torch.empty((B, K), dtype=torch.int32, device=dev)
             mgrad = torch.empty((B, K, 4 + C), dtype=torch.float32, device=dev)
-            _cabi.check(L.yl_loss_forward(rc.data_ptr(), lab.data_ptr(), B, F, K, C, int(l), anch, _cabi.ints(cfg['ANCHOR_MASK'][l]),
-                                          float(np.float32(ignore_thresh)), loss4.data_ptr(), gobj.data_ptr(), tcell.data_ptr(),
-                                          mcell.data_ptr(), mgrad.data_ptr(), None, _stream()))
+            calls.append((rc, F, int(l), gobj, tcell, mcell, mgrad))
             keep += [rc, gobj, tcell, mcell, mgrad]
+        for i, (rc, F, l, gobj, tcell, mcell, mgrad) in enumerate(calls):     # back to back: see _FusedYoloLoss.forward
+            fn = L.yl_loss_forward if i == 0 else L.yl_loss_forward_chained
+            _cabi.check(fn(rc.data_ptr(), lab.data_ptr(), B, F, K, C, l, anch, _cabi.ints(cfg['ANCHOR_MASK'][l]),
+                           float(np.float32(ignore_thresh)), loss4.data_ptr(), gobj.data_ptr(), tcell.data_ptr(),
+                           mcell.data_ptr(), mgrad.data_ptr(), None, _stream()))
     return loss4
