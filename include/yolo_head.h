@@ -201,6 +201,35 @@ int yl_context_destroy(yl_context *ctx);
 int yl_detect_host(yl_context *ctx, const float *const *raw_host, float conf_thre, float nms_thre,
                    float *out_rows_host, int *counts_host);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * (e) Multi-GPU: the final exchange of the image-sharded path            (no reference counterpart: the
+ *     reference validates on rank 0 only, yolo/engine/build.py:110-190, main_amp.py:175,207)
+ * One process per GPU; rank r owns B images and ends up with the detections of all world*B images (rank-major).  Each rank
+ * owns one device window (rows / counts / flags) that the peers map through CUDA IPC over NVLink; yl_xchg_push copies
+ * exactly counts[b] rows per image into every rank's window with plain peer stores (no collective, no staging, no host
+ * synchronisation), yl_xchg_wait blocks the stream until every rank's rows of that slot have landed, yl_xchg_release
+ * hands the slot back (a peer's next push into it waits for that).  All three are graph-capturable, so the exchange of
+ * step i runs under the kernels of step i+1 (double-buffered `slots`).
+ *   create   cap_out % 4 == 0 (row runs stay 16-byte aligned); slots in [1, 8]
+ *   handle   yl_xchg_handle_bytes() opaque bytes of this rank's window, to be all-gathered by the host (torch.distributed)
+ *   connect  handles = world * yl_xchg_handle_bytes() bytes, rank-major
+ *   push     rows [B, cap_out, 7] fp32 and counts [B] i32 as written by yl_nms (device, rows 16-byte aligned)
+ *   rows/counts  device pointers to THIS rank's gathered [world*B, cap_out, 7] / [world*B] of a slot
+ *   status   device int32: 0 ok, 1 = a push timed out waiting for a reader, 2 = a wait timed out waiting for a source
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct yl_xchg yl_xchg;
+int yl_xchg_create(yl_xchg **out, int device, int rank, int world, int B, long cap_out, int slots);
+int yl_xchg_destroy(yl_xchg *x);
+size_t yl_xchg_handle_bytes(void);
+int yl_xchg_local_handle(yl_xchg *x, void *handle);
+int yl_xchg_connect(yl_xchg *x, const void *handles);
+int yl_xchg_push(yl_xchg *x, const float *rows, const int *counts, int slot, yl_stream_t stream);
+int yl_xchg_wait(yl_xchg *x, int slot, yl_stream_t stream);
+int yl_xchg_release(yl_xchg *x, int slot, yl_stream_t stream);
+void *yl_xchg_rows(yl_xchg *x, int slot);
+void *yl_xchg_counts(yl_xchg *x, int slot);
+void *yl_xchg_status(yl_xchg *x);
+
 #ifdef __cplusplus
 }
 #endif

@@ -327,11 +327,95 @@ def gen_loss():
     np.savez_compressed(os.path.join(HERE, "loss.npz"), **out)
 
 
+def gen_fullsize():
+    """BASELINE-size pins without big files (configs 2, 3 and 4 at 608x608): the inputs are seeded (fullsize_inputs.py), the
+    decoded tensor is the oracle's (bit-equal to the CUDA decode, which the GPU test asserts), and what is stored is
+      * val setting (conf 1e-4, nms 0.4): per image the kept (box row, class) pairs of the REFERENCE postprocess in output
+        order + a SHA-256 of its output rows (the test rebuilds the rows from the pairs and the decoded tensor);
+      * detect setting (conf 0.2, nms 0.5): the reference's output rows;
+      * build_target at 50 GT/image, three layers: the reference's four dense tensors, stored sparse;
+      * raw -> detections through the reference's OWN decode (ATen sigmoid / exp) + postprocess: kept pairs, to be matched by
+        the fused CUDA path up to a counted set of threshold-borderline pairs."""
+    import hashlib
+    from oracle import oracle as orc
+    sys.path.insert(0, HERE)
+    import fullsize_inputs as fi
+    st = stable_utils()
+    raws = fi.raws_cpu()
+    pred = torch.from_numpy(orc.decode_eval_cat([r.numpy() for r in raws], fi.C))
+    out = {}
+
+    def kept_pairs(decoded, lst):
+        co = fi.corners_obj(decoded.numpy())
+        idx_all, cls_all = [], []
+        for b, o in enumerate(lst):
+            if o is None:
+                continue
+            lut = {}
+            for i, k in enumerate(co[b].view(np.uint32)):
+                lut.setdefault(k.tobytes(), []).append(i)
+            o = o.numpy()
+            for r in o:
+                cand = lut[r[:5].view(np.uint32).tobytes()]
+                cls = int(r[6])
+                hit = [i for i in cand if decoded[b, i, 5 + cls].numpy().view(np.uint32) == r[5:6].view(np.uint32)[0]]
+                assert len(hit) == 1, "ambiguous row -> box match"
+                idx_all.append(hit[0]); cls_all.append(cls)
+        return np.array(idx_all, np.int32), np.array(cls_all, np.int8)
+
+    for tag, conf, nmst in fi.SETTINGS:
+        a = ref_utils.postprocess(pred.clone(), fi.C, conf, nmst)
+        b = st.postprocess(pred.clone(), fi.C, conf, nmst)
+        ties = count_ties(pred, conf)
+        ca, ra = pack_list(a)
+        cb, rb = pack_list(b)
+        if ties == 0:
+            assert np.array_equal(ca, cb) and np.array_equal(ra, rb)
+        out[f"{tag}_ties"], out[f"{tag}_counts"] = np.int32(ties), cb
+        out[f"{tag}_unpatched_equal"] = np.int32(np.array_equal(ca, cb) and np.array_equal(ra, rb))
+        if tag == "det":
+            out["det_rows"] = rb
+        else:
+            ki, kc = kept_pairs(pred, b)
+            rebuilt = np.concatenate(fi.rows_from_kept(pred.numpy(), cb, ki, kc), 0)
+            assert np.array_equal(rebuilt.view(np.uint32), rb.view(np.uint32)), "rows_from_kept must rebuild the reference's rows"
+            out["val_kept_idx"], out["val_kept_cls"] = ki, kc
+            out["val_sha256"] = np.array(hashlib.sha256(np.ascontiguousarray(rb).tobytes()).hexdigest())
+        print(f"fullsize {tag}: rows {cb.tolist()} ties {ties} unpatched_equal {int(out[f'{tag}_unpatched_equal'])}")
+
+    # raw -> detections through the reference's own decode
+    dec_ref = ref_decode_eval(raws, fi.C)
+    conf, nmst = fi.SETTINGS[0][1], fi.SETTINGS[0][2]
+    lst = st.postprocess(dec_ref.clone(), fi.C, conf, nmst)
+    cr, _ = pack_list(lst)
+    ki, kc = kept_pairs(dec_ref, lst)
+    out["refdec_counts"], out["refdec_kept_idx"], out["refdec_kept_cls"] = cr, ki, kc
+    rel = (dec_ref - pred).abs() / pred.abs().clamp_min(1e-30)
+    out["refdec_max_rel"] = np.float64(rel.max().item())
+    print("fullsize raw->detections via the reference decode: rows", cr.tolist(), "max rel decode difference", float(rel.max()))
+
+    # build_target, 50 GT / image
+    labels = fi.labels_cpu()
+    crit = YOLOLoss(cfg(fi.C), ignore_thresh=0.7, device="cpu")
+    for l, r in enumerate(raws):
+        o, p = orc.decode_train(r.numpy(), l, fi.C)
+        p = fi.plant_pred(np.ascontiguousarray(p).copy(), labels.numpy(), l)
+        with torch.no_grad():
+            tgt, om, tm, ts = crit.build_target(torch.from_numpy(np.ascontiguousarray(o)), torch.from_numpy(p), l, labels.double())
+        for name, t, bg in (("target", tgt, 0.0), ("obj_mask", om, 1.0), ("tgt_mask", tm, 0.0), ("tgt_scale", ts, 0.0)):
+            idx, val = fi.sparse_pack(t.numpy(), bg)
+            out[f"bt{l}_{name}_idx"], out[f"bt{l}_{name}_val"] = idx.astype(np.int32 if idx.size == 0 or idx.max() < 2**31 else np.int64), val
+            out[f"bt{l}_{name}_shape"] = np.array(t.shape, np.int64)
+        print(f"fullsize build_target layer {l}: assigned cells={int(tm[..., 0].sum())} ignored={(om == 0).sum().item()}")
+    np.savez_compressed(os.path.join(HERE, "fullsize.npz"), **out)
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     only = sys.argv[1:]
     for name, fn in (("decode", gen_decode), ("postprocess", gen_postprocess), ("nms", gen_nms), ("iou", gen_iou),
-                     ("build_target", gen_build_target), ("epilogue", gen_epilogue), ("loss", gen_loss)):
+                     ("build_target", gen_build_target), ("epilogue", gen_epilogue), ("loss", gen_loss),
+                     ("fullsize", gen_fullsize)):
         if not only or name in only:
             fn()
     for f in sorted(os.listdir(HERE)):

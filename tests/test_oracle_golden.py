@@ -174,3 +174,81 @@ def test_loss_oracle_vs_reference_forward_and_autograd(golden_dir):
         assert np.allclose(grad, ref, rtol=2e-5, atol=1e-7), (l, np.abs(grad - ref).max())
         total += losses.sum()
     assert abs(total - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+
+
+# ------------------------------------------------------------------------------------------------ BASELINE-size pins
+def _fullsize(golden_dir):
+    import sys
+    if golden_dir not in sys.path:
+        sys.path.insert(0, golden_dir)
+    import fullsize_inputs as fi
+    return fi, _load(golden_dir, "fullsize.npz")
+
+
+def test_fullsize_postprocess_608_matches_reference(golden_dir):
+    """BASELINE configs 2 and 3 at 608x608 (val 1e-4 / 0.4 and detect 0.2 / 0.5): the oracle on its own decoded tensor against
+    the reference's postprocess on the same tensor (kept pairs + SHA-256 of the reference's rows; rows for the detect setting)."""
+    import hashlib
+    fi, g = _fullsize(golden_dir)
+    raws = [r.numpy() for r in fi.raws_cpu()]
+    pred = orc.decode_eval_cat(raws, fi.C)
+    for tag, conf, nmst in fi.SETTINGS:
+        got = orc.postprocess(pred, fi.C, conf, nmst, nthreads=4)
+        counts = g[f"{tag}_counts"]
+        assert [0 if o is None else len(o) for o in got] == counts.tolist()
+        rows = np.concatenate([o for o in got if o is not None], 0)
+        if tag == "det":
+            assert np.array_equal(rows.view(np.uint32), g["det_rows"].view(np.uint32))
+        else:
+            want = np.concatenate(fi.rows_from_kept(pred, counts, g["val_kept_idx"], g["val_kept_cls"]), 0)
+            assert hashlib.sha256(np.ascontiguousarray(want).tobytes()).hexdigest() == str(g["val_sha256"])
+            assert np.array_equal(rows.view(np.uint32), want.view(np.uint32))
+    # raw -> detections: the reference's own decode (ATen sigmoid / exp) leads to the same kept pairs up to borderline ones
+    fused = orc.detect(raws, fi.C, fi.SETTINGS[0][1], fi.SETTINGS[0][2], nthreads=4)
+    _check_refdec(fi, g, pred, fused)
+
+
+def _check_refdec(fi, g, pred, got_rows):
+    """Kept (box, class) pairs of a raw -> detections run against those of the reference decode + postprocess.  The two decodes
+    differ by <= 2.1e-7 relative, so a pair may flip only when its score is within 1e-5 relative of conf or an IoU within 1e-5 of the
+    NMS threshold; the flips are counted and bounded, not ignored."""
+    co = fi.corners_obj(pred)
+    o = 0
+    flips = 0
+    for b, n in enumerate(g["refdec_counts"]):
+        want = set(zip(g["refdec_kept_idx"][o:o + n].tolist(), g["refdec_kept_cls"][o:o + n].tolist()))
+        o += n
+        lut = {k.tobytes(): i for i, k in enumerate(co[b].view(np.uint32))}
+        r = got_rows[b]
+        have = set((lut[x[:5].view(np.uint32).tobytes()], int(x[6])) for x in np.ascontiguousarray(r))
+        flips += len(want ^ have)
+    assert float(g["refdec_max_rel"]) <= 1e-5
+    assert flips <= 4, "%d kept pairs differ between the reference-decoded and the spec-decoded run" % flips
+    return flips
+
+
+@pytest.mark.parametrize("layer", [0, 1, 2])
+def test_fullsize_build_target_608_matches_reference(golden_dir, layer):
+    """BASELINE config 4 at 608x608, 50 GT / image (B=2 of it): the reference's four dense tensors, stored sparse."""
+    fi, g = _fullsize(golden_dir)
+    raws = fi.raws_cpu()
+    labels = fi.labels_cpu().numpy()
+    _, p = orc.decode_train(raws[layer].numpy(), layer, fi.C)
+    p = fi.plant_pred(np.ascontiguousarray(p).copy(), labels, layer)
+    got = orc.build_target(p, labels, layer, fi.C, 0.7)
+    _check_fullsize_bt(fi, g, layer, got)
+
+
+def _check_fullsize_bt(fi, g, layer, got):
+    for name, t, bg in zip(("target", "obj_mask", "tgt_mask", "tgt_scale"), got, (0.0, 1.0, 0.0, 0.0)):
+        want = fi.sparse_unpack(tuple(g[f"bt{layer}_{name}_shape"]), bg, g[f"bt{layer}_{name}_idx"], g[f"bt{layer}_{name}_val"])
+        t = np.asarray(t)
+        assert t.shape == want.shape
+        if name == "target":
+            sel = np.ones(t.shape[-1], bool)
+            sel[2:4] = False                        # log() targets: 1e-5 relative (north_star), everything else bit-exact
+            assert np.array_equal(t[..., sel], want[..., sel])
+            np.testing.assert_allclose(t[..., 2:4], want[..., 2:4], rtol=1e-5, atol=1e-6)
+        else:
+            assert np.array_equal(t, want, equal_nan=True), name
+    assert (np.asarray(got[1]) == 0).sum() > 0 and np.asarray(got[2]).sum() > 0

@@ -85,6 +85,27 @@ def lib():
     L.yl_context_destroy.argtypes = [_p]
     L.yl_detect_host.restype = _i
     L.yl_detect_host.argtypes = [_p, _p, _f, _f, _p, _p]
+    L.yl_xchg_create.restype = _i
+    L.yl_xchg_create.argtypes = [ctypes.POINTER(_p), _i, _i, _i, _i, _l, _i]
+    L.yl_xchg_destroy.restype = _i
+    L.yl_xchg_destroy.argtypes = [_p]
+    L.yl_xchg_handle_bytes.restype = _sz
+    L.yl_xchg_handle_bytes.argtypes = []
+    L.yl_xchg_local_handle.restype = _i
+    L.yl_xchg_local_handle.argtypes = [_p, _p]
+    L.yl_xchg_connect.restype = _i
+    L.yl_xchg_connect.argtypes = [_p, _p]
+    L.yl_xchg_push.restype = _i
+    L.yl_xchg_push.argtypes = [_p, _p, _p, _i, _p]
+    L.yl_xchg_wait.restype = _i
+    L.yl_xchg_wait.argtypes = [_p, _i, _p]
+    L.yl_xchg_release.restype = _i
+    L.yl_xchg_release.argtypes = [_p, _i, _p]
+    for name in ("yl_xchg_rows", "yl_xchg_counts"):
+        getattr(L, name).restype = _p
+        getattr(L, name).argtypes = [_p, _i]
+    L.yl_xchg_status.restype = _p
+    L.yl_xchg_status.argtypes = [_p]
     if L.yl_abi_version() != 1:
         raise YoloHeadError("libyolohead.so ABI version mismatch")
     _lib = L
@@ -96,6 +117,8 @@ EXPORTS = [
     "yl_post_workspace_bytes", "yl_post_reset", "yl_filter_raw", "yl_filter_raw_stage", "yl_filter_dense", "yl_nms", "yl_build_target", "yl_coco_rows",
     "yl_loss_forward", "yl_loss_forward_chained", "yl_loss_backward",
     "yl_context_create", "yl_context_destroy", "yl_detect_host",
+    "yl_xchg_create", "yl_xchg_destroy", "yl_xchg_handle_bytes", "yl_xchg_local_handle", "yl_xchg_connect", "yl_xchg_push",
+    "yl_xchg_wait", "yl_xchg_release", "yl_xchg_rows", "yl_xchg_counts", "yl_xchg_status",
 ]
 
 

@@ -12,6 +12,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
+#include <vector>
+
 #include "yl_common.cuh"
 #include "../../include/yolo_head.h"
 
@@ -757,64 +760,70 @@ k_filter_raw_tma(const __grid_constant__ RawParams P, const __grid_constant__ Tm
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Warp-specialised form (default where the big scales are TMA-capable): ONE persistent kernel, one CTA per SM, three
-// kinds of warps that never wait for each other's memory latency:
+// Warp-specialised form (YL_FILTER=ws): ONE persistent kernel, one CTA per SM, two kinds of warps that never wait for each
+// other's memory latency:
 //   * streaming warps   private TMA rings ([WT_KC class planes x 128 boxes] per stage, UTMALDG.2D + transaction
-//                       mbarriers) exactly as above, but a finished tile (flag words + sigmoid(objectness), 2 KB) is
-//                       handed over through a shared-memory packet instead of being resolved in place, so the ring never
-//                       drains while a warp follows the dependent round trips of the exact pass;
-//   * emit warps        WS_EPS per streaming warp: wait for a packet, run the exact pass (emit_pairs: flagged logits and
-//                       box planes come back from L2 microseconds after the ring streamed them, slot atomics, 32-byte
-//                       records), give the packet back;
-//   * scalar warps      the scales whose planes are not 16-byte aligned (19x19: 4.8 % of the bytes) with register-staged
-//                       loads, stream + emit in the same warp, from their own tile counter.
-// No flag table or objectness table goes through global memory and there is no separate emit launch.
+//                       mbarriers) as above, plus a [5 planes x 128 boxes] box of tx,ty,tw,th,objectness per tile.  A class
+//                       logit that passes the conservative bound is copied out of the ring stage while it is on-chip
+//                       (box slot, class, logit) into the tile's packet; at the end of the tile the packet also gets
+//                       sigmoid(objectness) and the raw tx,ty,tw,th of the tile's boxes from registers and is handed over.
+//                       The ring never drains while somebody follows the dependent round trips of the exact pass.
+//   * emit warps        one per streaming warp, WS_PK packets in flight: exact spec-math test of the queued pairs, NaN rule,
+//                       one decode per surviving box, slot atomics, 32-byte records.  No global load at all: nothing the
+//                       stream brought on-chip is fetched a second time (k_emit_flagged reads 133 MB of scattered sectors).
+//                       A tile with more queued pairs than the packet holds (dense inputs) falls back to the flag-word
+//                       form of emit_pairs, which re-reads the logits.
+// The scales whose planes are not 16-byte aligned (19x19: 4.8 % of the bytes) cannot be fetched by TMA; they go through
+// k_flag_raw + k_emit_flagged on a forked side stream and run next to this kernel.
 // ---------------------------------------------------------------------------------------------------------------
 #ifndef YL_WS_STREAM
-#define YL_WS_STREAM 4
+#define YL_WS_STREAM 6
 #endif
-#ifndef YL_WS_EPS
-#define YL_WS_EPS 2
+#ifndef YL_WS_PK
+#define YL_WS_PK 2
 #endif
 #ifndef YL_WS_STAGES
-#define YL_WS_STAGES 4
+#define YL_WS_STAGES 3
 #endif
-#ifndef YL_WS_SCALAR
-#define YL_WS_SCALAR 4
+#ifndef YL_WS_MAXREG
+#define YL_WS_MAXREG 96                        // register cap: one CTA per SM must leave room for the side stream's CTAs
 #endif
-#ifndef YL_WS_MINB
-#define YL_WS_MINB 2                           // register cap = 65536 / (WS_THREADS * YL_WS_MINB): leaves room for co-resident NMS CTAs
+#ifndef YL_WS_SLEEP
+#define YL_WS_SLEEP 100
 #endif
-constexpr int WS_STREAM = YL_WS_STREAM;        // streaming warps per CTA
-constexpr int WS_EPS = YL_WS_EPS;              // emit warps (= packets) per streaming warp
+constexpr int WS_STREAM = YL_WS_STREAM;        // streaming warps per CTA (= emit warps)
+constexpr int WS_PK = YL_WS_PK;                // packets per streaming warp
 constexpr int WS_STAGES = YL_WS_STAGES;        // ring stages per streaming warp (4 KB each)
-constexpr int WS_SCALAR = YL_WS_SCALAR;        // scalar warps per CTA
-constexpr int WS_EMIT = WS_STREAM * WS_EPS;
-constexpr int WS_THREADS = 32 * (WS_STREAM + WS_EMIT + WS_SCALAR);
+constexpr int WS_THREADS = 32 * 2 * WS_STREAM;
+constexpr int WS_QCAP = 256;                   // queued (box slot, class, logit) entries per packet
+constexpr int WS_HEAD = 5;                     // planes of the per-tile head box: tx, ty, tw, th, objectness
 
 template <int NW>
 struct alignas(16) WsPacket {
-    unsigned bits[NW][WT_BOX];                 // flagged-class words per box slot of the tile
+    float4 box[WT_BOX];                        // raw (tx,ty,tw,th) per box slot; the emit warp decodes surviving boxes in place
     float sobj[WT_BOX];                        // sigmoid(objectness) per box slot
-    int layer, ba, p0, vec;                    // vec = 0: no more tiles
+    float val[WS_QCAP];                        // queued class logits; sigmoid(logit) of the passing ones after the exact test
+    unsigned bits[NW][WT_BOX];                 // flagged-class words per box slot (overflow fallback)
+    unsigned short ent[WS_QCAP];               // bit15 pass | box slot (7b) << 8 | class (7b)
+    unsigned any[4], nan[4];                   // per box slot: has a surviving pair / has a NaN class logit
+    unsigned n;                                // queued entries (may exceed WS_QCAP: then the fallback path runs)
+    int layer, ba, p0, stop;
 };
 struct alignas(128) WsStream {
     float stage[WS_STAGES][WT_KC][WT_BOX];
-    float objp[2][WT_BOX];                     // objectness plane of the current / the next tile
-    unsigned long long full[WS_STAGES], obj_full[2];
+    float head[2][WS_HEAD][WT_BOX];            // tx,ty,tw,th,obj planes of the current / the next tile
+    unsigned long long full[WS_STAGES], head_full[2];
 };
 template <int NW>
 struct WsSmem {
     WsStream s[WS_STREAM];
-    WsPacket<NW> pk[WS_EMIT];
-    EmitWarp em[WS_EMIT + WS_SCALAR];
-    float sobj_sc[WS_SCALAR > 0 ? WS_SCALAR : 1][32];
-    unsigned long long pk_full[WS_EMIT], pk_empty[WS_EMIT];
+    WsPacket<NW> pk[WS_STREAM][WS_PK];
+    EmitWarp em[WS_STREAM];                    // scratch of the overflow fallback
+    unsigned long long pk_full[WS_STREAM][WS_PK], pk_empty[WS_STREAM][WS_PK];
 };
+struct TmaMapsWs { CUtensorMap cls[3], head[3]; };
+static_assert(sizeof(WsSmem<4>) <= 227 * 1024, "the warp-specialised CTA must fit one SM's shared memory");
 
-#ifndef YL_WS_SLEEP
-#define YL_WS_SLEEP 200
-#endif
 // Wait of a warp that has nothing else to do (emit warps between packets): back off between polls so that the spinning
 // does not take issue slots from the streaming warps of the same scheduler.
 __device__ __forceinline__ void mbar_wait_idle(unsigned long long *bar, unsigned parity)
@@ -832,8 +841,7 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// t-th tile among the scales with layer.tma == tma (P.layer[] of this form holds every scale; layer[l].tiles = warp
-// tiles per (image, anchor)); np == 0: no such tile.
+// t-th tile among the scales with layer.tma == tma (layer[l].tiles = warp tiles per (image, anchor)); np == 0: no such tile.
 __device__ __forceinline__ WtTile ws_tile(const RawParams &P, int t, int nba, int tma)
 {
     WtTile T;
@@ -856,35 +864,109 @@ __device__ __forceinline__ WtTile ws_tile(const RawParams &P, int t, int nba, in
     return T;
 }
 
-// Streaming warp -> emit warp: packet e = warp * WS_EPS + (n_sent mod WS_EPS); a tile without a flagged pair sends nothing.
+// Exact pass over a packet whose pairs were queued with their logits: no global load.
 template <int NW>
-__device__ __forceinline__ void ws_send(WsSmem<NW> &S, int warp, unsigned &n_sent, int layer, int ba, int p0,
-                                        const float (&obj)[4], const unsigned (&bits)[4][NW])
+__device__ __forceinline__ void emit_packet(const RawParams &P, const RawLayer &Ly, WsPacket<NW> &K, int n)
 {
     const int lane = threadIdx.x & 31;
-    unsigned any = 0u;
-#pragma unroll
-    for (int v = 0; v < 4; ++v)
-#pragma unroll
-        for (int w = 0; w < NW; ++w) any |= bits[v][w];
-    if (!__any_sync(0xFFFFFFFFu, any != 0u)) return;
-    const int e = warp * WS_EPS + (int)(n_sent % WS_EPS);
-    mbar_wait(&S.pk_empty[e], ((n_sent / WS_EPS) & 1u) ^ 1u);       // first use: passes on the fresh barrier
-    WsPacket<NW> &K = S.pk[e];
-    *reinterpret_cast<float4 *>(&K.sobj[lane * 4]) = make_float4(obj[0], obj[1], obj[2], obj[3]);
-#pragma unroll
-    for (int w = 0; w < NW; ++w)
-        *reinterpret_cast<uint4 *>(&K.bits[w][lane * 4]) = make_uint4(bits[0][w], bits[1][w], bits[2][w], bits[3][w]);
-    if (lane == 0) { K.layer = layer; K.ba = ba; K.p0 = p0; K.vec = 4; }
+    const int C = P.C;
+    const float thr = P.thr;
+    const int b = K.ba / 3, a = K.ba - 3 * b;
+    const int row_base = Ly.row_off + a * Ly.F2 + K.p0;                // + box slot = row inside the image
+    for (int q = lane; q < n; q += 32) {
+        const unsigned en = K.ent[q];
+        const float t = K.val[q];
+        const int bs = en >> 8;
+        // a NaN class logit makes torch.max (utils.py:139) NaN and drops the whole row (:145)
+        if (t != t) atomicOr(&K.nan[bs >> 5], 1u << (bs & 31));
+        const float cls = spec_sigmoidf(t);
+        if (__fmul_rn(K.sobj[bs], cls) >= thr) {                        // utils.py:170
+            atomicOr(&K.any[bs >> 5], 1u << (bs & 31));
+            K.val[q] = cls;
+            K.ent[q] = (unsigned short)(en | 0x8000u);
+        }
+    }
     __syncwarp();
-    if (lane == 0) mbar_arrive(&S.pk_full[e]);
-    ++n_sent;
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {                                        // one decode per surviving box (yololayer.py:150-162)
+        const int bs = 32 * j + lane;
+        if (((K.any[j] & ~K.nan[j]) >> lane) & 1u) {
+            const float4 r = K.box[bs];
+            K.box[bs] = decode_box_v(r.x, r.y, r.z, r.w, Ly.Fw, K.p0 + bs, Ly.aw[a], Ly.ah[a], Ly.stride);
+        }
+    }
+    __syncwarp();
+    for (int q0 = 0; q0 < n; q0 += 128) {
+        unsigned slot[4], en[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {                                    // the slot atomics of four entries are in flight together
+            const int q = q0 + 32 * u + lane;
+            en[u] = 0u;
+            slot[u] = 0xFFFFFFFFu;
+            if (q < n) {
+                en[u] = K.ent[q];
+                const int bs = (en[u] >> 8) & 0x7F;
+                if ((en[u] & 0x8000u) && !((K.nan[bs >> 5] >> (bs & 31)) & 1u))
+                    slot[u] = atomicAdd(&P.seg_count[(unsigned)(b * C + (int)(en[u] & 0x7F))], 1u);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (slot[u] < (unsigned)P.cap_seg) {
+                const int q = q0 + 32 * u + lane;
+                const int bs = (en[u] >> 8) & 0x7F;
+                const float cls = K.val[q];
+                const float so = K.sobj[bs];
+                const float s = __fadd_rn(__fmul_rn(so, cls), 0.0f);       // +0 canonicalises -0
+                const unsigned seg = (unsigned)(b * C + (int)(en[u] & 0x7F));
+                uint4 *r = P.cand + ((size_t)seg * P.cap_seg + slot[u]) * 2;
+                const float4 bx = K.box[bs];
+                r[0] = make_uint4(__float_as_uint(s), (unsigned)(row_base + bs), __float_as_uint(cls), __float_as_uint(so));
+                r[1] = make_uint4(__float_as_uint(bx.x), __float_as_uint(bx.y), __float_as_uint(bx.z), __float_as_uint(bx.w));
+            }
+        }
+    }
+}
+
+// Queue this lane's flagged (box slot, class, logit) entries of one chunk; sp = the lane's first box in the stage.
+// Not inlined: the streaming loop stays small, and only the lanes that flagged something come here.
+__device__ __noinline__ void ws_capture(unsigned *n, unsigned short *ent, float *val, const float *sp,
+                                        unsigned a0, unsigned a1, unsigned a2, unsigned a3, int slot0, int cls0)
+{
+#pragma unroll 1
+    for (int v = 0; v < 4; ++v) {
+        unsigned m = (v == 0) ? a0 : ((v == 1) ? a1 : ((v == 2) ? a2 : a3));
+        while (m) {
+            const int k = __ffs(m) - 1;
+            m &= m - 1u;
+            const unsigned q = atomicAdd(n, 1u);
+            if (q < (unsigned)WS_QCAP) {
+                ent[q] = (unsigned short)(((slot0 + v) << 8) | (cls0 + k));
+                val[q] = sp[k * WT_BOX + v];
+            }
+        }
+    }
+}
+
+// Overflow path of an emit warp (cold): the packet's flag words through the re-reading form of the exact pass.
+template <int NW>
+__device__ __noinline__ void ws_fallback(const RawParams &P, WsPacket<NW> &K, EmitWarp &E)
+{
+    const int lane = threadIdx.x & 31;
+    float lth[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    unsigned bits[4][NW];
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+        const uint4 m = *reinterpret_cast<const uint4 *>(&K.bits[w][lane * 4]);
+        bits[0][w] = m.x; bits[1][w] = m.y; bits[2][w] = m.z; bits[3][w] = m.w;
+    }
+    emit_pairs<4, NW>(P, P.layer[K.layer], K.ba, K.p0, lth, bits, E, K.sobj);
 }
 
 template <int NW>
-__global__ void __launch_bounds__(WS_THREADS, YL_WS_MINB)
-k_filter_raw_ws(const __grid_constant__ RawParams P, const __grid_constant__ TmaMaps maps, int nba,
-                unsigned *__restrict__ tile_counter, unsigned *__restrict__ scalar_counter)
+__global__ void __maxnreg__(YL_WS_MAXREG)
+k_filter_raw_ws(const __grid_constant__ RawParams P, const __grid_constant__ TmaMapsWs maps, int nba,
+                unsigned *__restrict__ tile_counter)
 {
     extern __shared__ __align__(128) unsigned char ws_smem_raw[];
     WsSmem<NW> &S = *reinterpret_cast<WsSmem<NW> *>(ws_smem_raw);
@@ -895,10 +977,10 @@ k_filter_raw_ws(const __grid_constant__ RawParams P, const __grid_constant__ Tma
     if (threadIdx.x == 0) {
         for (int w = 0; w < WS_STREAM; ++w) {
             for (int s = 0; s < WS_STAGES; ++s) mbar_init(&S.s[w].full[s], 1);
-            mbar_init(&S.s[w].obj_full[0], 1);
-            mbar_init(&S.s[w].obj_full[1], 1);
+            mbar_init(&S.s[w].head_full[0], 1);
+            mbar_init(&S.s[w].head_full[1], 1);
+            for (int k = 0; k < WS_PK; ++k) { mbar_init(&S.pk_full[w][k], 1); mbar_init(&S.pk_empty[w][k], 1); }
         }
-        for (int e = 0; e < WS_EMIT; ++e) { mbar_init(&S.pk_full[e], 1); mbar_init(&S.pk_empty[e], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -908,43 +990,51 @@ k_filter_raw_ws(const __grid_constant__ RawParams P, const __grid_constant__ Tma
         // ---------------- streaming warp ----------------
         WsStream &W = S.s[warp];
         const int n_cc = (C + WT_KC - 1) / WT_KC;                    // class chunks per tile (>= WS_STAGES, host-checked)
-        unsigned n_sent = 0u;
         auto issue_chunk = [&](const WtTile &T, int c, int s) {
             mbar_expect_tx(&W.full[s], WT_KC * WT_BOX * 4u);         // full box, zero fill included
-            tma_load_2d(&W.stage[s][0][0], &maps.m[T.layer], T.p0, T.row0 + c * WT_KC, &W.full[s]);
+            tma_load_2d(&W.stage[s][0][0], &maps.cls[T.layer], T.p0, T.row0 + c * WT_KC, &W.full[s]);
         };
-        auto issue_obj = [&](const WtTile &T, int slot) {
-            const unsigned bytes = (unsigned)T.np * 4u;
-            mbar_expect_tx(&W.obj_full[slot], bytes);
-            bulk_g2s(&W.objp[slot][0], T.src + 4 * (size_t)P.layer[T.layer].F2, bytes, &W.obj_full[slot]);
+        auto issue_head = [&](const WtTile &T, int slot) {
+            mbar_expect_tx(&W.head_full[slot], WS_HEAD * WT_BOX * 4u);
+            tma_load_2d(&W.head[slot][0][0], &maps.head[T.layer], T.p0, T.row0 - 5, &W.head_full[slot]);
         };
         // the tile counter's round trip is taken one tile ahead: `ahead` is the ticket of the tile after `nxt`, drawn at
         // the top of an iteration and first used at its bottom
-#ifdef YL_WS_STATIC                                                       // (diagnostic build: round-robin tiles, no counter)
-        int static_next = blockIdx.x * WS_STREAM + warp;
-        auto draw = [&]() { const int t = static_next; static_next += gridDim.x * WS_STREAM; return t; };
-#else
         auto draw = [&]() { int t = 0; if (lane == 0) t = (int)atomicAdd(tile_counter, 1u); return t; };
-#endif
         auto resolve = [&](int t) { return ws_tile(P, __shfl_sync(FULL, t, 0), nba, 1); };
         WtTile cur = resolve(draw());
         WtTile nxt = cur;
         if (cur.np != 0) nxt = resolve(draw());
         if (lane == 0 && cur.np != 0) {
-            issue_obj(cur, 0);
+            issue_head(cur, 0);
             for (int c = 0; c < WS_STAGES; ++c) issue_chunk(cur, c, c);
         }
         int s = 0;                       // ring stage of the next chunk to consume
         unsigned ph = 0u;                // phase bit per ring stage
-        unsigned it = 0u;                // tiles processed (objectness slot = it & 1, its phase = (it >> 1) & 1)
+        unsigned it = 0u;                // tiles processed (head slot = it & 1, its phase = (it >> 1) & 1)
+        unsigned n_sent = 0u;            // packets handed over
+        bool have_pk = false;            // packet n_sent % WS_PK is already ours (acquired, n == 0)
         while (cur.np != 0) {
             const int ahead = (nxt.np != 0) ? draw() : 0;
-            if (lane == 0 && nxt.np != 0) issue_obj(nxt, (it + 1) & 1);
+            if (lane == 0 && nxt.np != 0) issue_head(nxt, (it + 1) & 1);
+            const int kslot = (int)(n_sent % WS_PK);
+            WsPacket<NW> &K = S.pk[warp][kslot];
+            if (!have_pk) {
+                mbar_wait(&S.pk_empty[warp][kslot], ((n_sent / WS_PK) & 1u) ^ 1u);      // first use: passes on the fresh barrier
+                if (lane == 0) K.n = 0u;
+                have_pk = true;
+            }
             const bool inb = lane * 4 < cur.np;
             float obj[4], lth[4];
+            float4 braw[4];
             {
-                mbar_wait(&W.obj_full[it & 1], (it >> 1) & 1u);
-                const float4 to = *reinterpret_cast<const float4 *>(&W.objp[it & 1][lane * 4]);
+                mbar_wait(&W.head_full[it & 1], (it >> 1) & 1u);
+                const float *hp = &W.head[it & 1][0][lane * 4];
+                const float4 tx = *reinterpret_cast<const float4 *>(hp), ty = *reinterpret_cast<const float4 *>(hp + WT_BOX);
+                const float4 tw = *reinterpret_cast<const float4 *>(hp + 2 * WT_BOX), th = *reinterpret_cast<const float4 *>(hp + 3 * WT_BOX);
+                const float4 to = *reinterpret_cast<const float4 *>(hp + 4 * WT_BOX);
+                braw[0] = make_float4(tx.x, ty.x, tw.x, th.x); braw[1] = make_float4(tx.y, ty.y, tw.y, th.y);
+                braw[2] = make_float4(tx.z, ty.z, tw.z, th.z); braw[3] = make_float4(tx.w, ty.w, tw.w, th.w);
                 const float tv[4] = {to.x, to.y, to.z, to.w};
 #pragma unroll
                 for (int v = 0; v < 4; ++v) {
@@ -952,116 +1042,108 @@ k_filter_raw_ws(const __grid_constant__ RawParams P, const __grid_constant__ Tma
                     lth[v] = inb ? class_logit_bound(obj[v], P.thr) : kInf;
                 }
             }
-            unsigned bits[4][NW];
-#pragma unroll
-            for (int w = 0; w < NW; ++w) {
-                unsigned m0 = 0u, m1 = 0u, m2 = 0u, m3 = 0u;
+            __syncwarp();                                              // K.n = 0 is visible; the head slot has been read
+            // One flat loop over the class chunks (not unrolled over the flag words: the kernel must stay inside the instruction
+            // cache, its two roles run different code on the same SM); a finished flag word goes straight into the packet.
+            constexpr int CPW = 32 / WT_KC;                              // chunks per flag word
+            unsigned m0 = 0u, m1 = 0u, m2 = 0u, m3 = 0u;
 #pragma unroll 1
-                for (int cc = 0; cc < 32 / WT_KC; ++cc) {
-                    const int c = w * (32 / WT_KC) + cc;                 // class chunk index
-                    if (c >= n_cc) break;                                // warp-uniform
-                    mbar_wait(&W.full[s], (ph >> s) & 1u);
-                    const int kn = min(WT_KC, C - c * WT_KC);
-                    const float *sp = &W.stage[s][0][lane * 4];
-                    unsigned a0 = 0u, a1 = 0u, a2 = 0u, a3 = 0u;
-#ifndef YL_WS_NOCOMPARE                                                  // (diagnostic build: the TMA ring alone)
-                    if (kn == WT_KC) {
-                        // full chunk (every chunk when C is a multiple of WT_KC): all LDS.128 issued before the first compare
-                        float4 tv[WT_KC];
+            for (int c = 0; c < n_cc; ++c) {
+                mbar_wait(&W.full[s], (ph >> s) & 1u);
+                const int kn = min(WT_KC, C - c * WT_KC);
+                const float *sp = &W.stage[s][0][lane * 4];
+                unsigned a0 = 0u, a1 = 0u, a2 = 0u, a3 = 0u;
+                if (kn == WT_KC) {
+                    // full chunk (every chunk when C is a multiple of WT_KC): all LDS.128 issued before the first compare
+                    float4 tv[WT_KC];
 #pragma unroll
-                        for (int k = 0; k < WT_KC; ++k) tv[k] = *reinterpret_cast<const float4 *>(sp + k * WT_BOX);
+                    for (int k = 0; k < WT_KC; ++k) tv[k] = *reinterpret_cast<const float4 *>(sp + k * WT_BOX);
 #pragma unroll
-                        for (int k = 0; k < WT_KC; ++k) {
-                            flag_or(a0, tv[k].x, lth[0], 1u << k);
-                            flag_or(a1, tv[k].y, lth[1], 1u << k);
-                            flag_or(a2, tv[k].z, lth[2], 1u << k);
-                            flag_or(a3, tv[k].w, lth[3], 1u << k);
-                        }
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < WT_KC; ++k)
-                            if (k < kn) {
-                                const float4 tv = *reinterpret_cast<const float4 *>(sp + k * WT_BOX);
-                                flag_or(a0, tv.x, lth[0], 1u << k);
-                                flag_or(a1, tv.y, lth[1], 1u << k);
-                                flag_or(a2, tv.z, lth[2], 1u << k);
-                                flag_or(a3, tv.w, lth[3], 1u << k);
-                            }
+                    for (int k = 0; k < WT_KC; ++k) {
+                        flag_or(a0, tv[k].x, lth[0], 1u << k);
+                        flag_or(a1, tv[k].y, lth[1], 1u << k);
+                        flag_or(a2, tv[k].z, lth[2], 1u << k);
+                        flag_or(a3, tv[k].w, lth[3], 1u << k);
                     }
-#endif
-                    const int sh = cc * WT_KC;
-                    m0 |= a0 << sh; m1 |= a1 << sh; m2 |= a2 << sh; m3 |= a3 << sh;
-                    __syncwarp();                                        // every lane has read the stage
-                    if (lane == 0) {
-                        const int cn = c + WS_STAGES;                    // the chunk that takes this stage next
-                        if (cn < n_cc) issue_chunk(cur, cn, s);
-                        else if (nxt.np != 0) issue_chunk(nxt, cn - n_cc, s);
+                } else {
+#pragma unroll 1
+                    for (int k = 0; k < kn; ++k) {
+                        const float4 tv = *reinterpret_cast<const float4 *>(sp + k * WT_BOX);
+                        flag_or(a0, tv.x, lth[0], 1u << k);
+                        flag_or(a1, tv.y, lth[1], 1u << k);
+                        flag_or(a2, tv.z, lth[2], 1u << k);
+                        flag_or(a3, tv.w, lth[3], 1u << k);
                     }
-                    ph ^= 1u << s;
-                    s = (s + 1 == WS_STAGES) ? 0 : s + 1;
                 }
                 // a dead box (objectness below the threshold, or outside the tile) flags nothing, whatever its logits are
-                bits[0][w] = (lth[0] == kInf) ? 0u : m0; bits[1][w] = (lth[1] == kInf) ? 0u : m1;
-                bits[2][w] = (lth[2] == kInf) ? 0u : m2; bits[3][w] = (lth[3] == kInf) ? 0u : m3;
+                if (lth[0] == kInf) a0 = 0u;
+                if (lth[1] == kInf) a1 = 0u;
+                if (lth[2] == kInf) a2 = 0u;
+                if (lth[3] == kInf) a3 = 0u;
+                // rare (~0.6 % of the logits): queue (box slot, class, logit) while the logit is still in the stage
+                if (a0 | a1 | a2 | a3) ws_capture(&K.n, K.ent, K.val, sp, a0, a1, a2, a3, lane * 4, c * WT_KC);
+                const int sh = (c % CPW) * WT_KC;
+                m0 |= a0 << sh; m1 |= a1 << sh; m2 |= a2 << sh; m3 |= a3 << sh;
+                __syncwarp();                                            // every lane has read the stage
+                if (lane == 0) {
+                    const int cn = c + WS_STAGES;                        // the chunk that takes this stage next
+                    if (cn < n_cc) issue_chunk(cur, cn, s);
+                    else if (nxt.np != 0) issue_chunk(nxt, cn - n_cc, s);
+                }
+                ph ^= 1u << s;
+                s = (s + 1 == WS_STAGES) ? 0 : s + 1;
+                if ((c + 1) % CPW == 0 || c + 1 == n_cc) {
+                    *reinterpret_cast<uint4 *>(&K.bits[c / CPW][lane * 4]) = make_uint4(m0, m1, m2, m3);
+                    m0 = m1 = m2 = m3 = 0u;
+                }
             }
-            ws_send<NW>(S, warp, n_sent, cur.layer, cur.ba, cur.p0, obj, bits);
+            __syncwarp();
+            // hand the tile over (the loop's last __syncwarp made every lane's queue entries and K.n visible)
+            if (*reinterpret_cast<volatile unsigned *>(&K.n) != 0u) {    // warp-uniform
+                *reinterpret_cast<float4 *>(&K.sobj[lane * 4]) = make_float4(obj[0], obj[1], obj[2], obj[3]);
+#pragma unroll
+                for (int v = 0; v < 4; ++v) K.box[lane * 4 + v] = braw[v];
+                if (lane < 4) { K.any[lane] = 0u; K.nan[lane] = 0u; }
+                if (lane == 0) { K.layer = cur.layer; K.ba = cur.ba; K.p0 = cur.p0; K.stop = 0; }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&S.pk_full[warp][kslot]);
+                ++n_sent;
+                have_pk = false;
+            }
             cur = nxt;
             if (nxt.np != 0) nxt = resolve(ahead);
             ++it;
         }
-        for (int k = 0; k < WS_EPS; ++k) {                              // tell this warp's emit warps to stop
-            const int e = warp * WS_EPS + (int)(n_sent % WS_EPS);
-            mbar_wait(&S.pk_empty[e], ((n_sent / WS_EPS) & 1u) ^ 1u);
-            if (lane == 0) S.pk[e].vec = 0;
+        {                                                               // tell the emit warp to stop
+            const int kslot = (int)(n_sent % WS_PK);
+            if (!have_pk) mbar_wait(&S.pk_empty[warp][kslot], ((n_sent / WS_PK) & 1u) ^ 1u);
+            if (lane == 0) S.pk[warp][kslot].stop = 1;
             __syncwarp();
-            if (lane == 0) mbar_arrive(&S.pk_full[e]);
-            ++n_sent;
-        }
-    } else if (warp < WS_STREAM + WS_EMIT) {
-        // ---------------- emit warp ----------------
-        const int e = warp - WS_STREAM;
-        WsPacket<NW> &K = S.pk[e];
-        EmitWarp &E = S.em[e];
-        for (unsigned n = 0u;; ++n) {
-            mbar_wait_idle(&S.pk_full[e], n & 1u);
-            if (K.vec == 0) break;                                       // warp-uniform
-#ifdef YL_WS_NOEMIT                                                      // diagnostic build: the streaming side alone
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&S.pk_empty[e]);
-            continue;
-#endif
-            float lth[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-            unsigned bits[4][NW];
-#pragma unroll
-            for (int w = 0; w < NW; ++w) {
-                const uint4 m = *reinterpret_cast<const uint4 *>(&K.bits[w][lane * 4]);
-                bits[0][w] = m.x; bits[1][w] = m.y; bits[2][w] = m.z; bits[3][w] = m.w;
-            }
-            emit_pairs<4, NW>(P, P.layer[K.layer], K.ba, K.p0, lth, bits, E, K.sobj);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&S.pk_empty[e]);
+            if (lane == 0) mbar_arrive(&S.pk_full[warp][kslot]);
         }
     } else {
-        // ---------------- scalar warp ----------------
-        const int k = warp - WS_STREAM - WS_EMIT;
-        EmitWarp &E = S.em[WS_EMIT + k];
-        float *sobj1 = S.sobj_sc[k];
-        for (;;) {
-            int t = 0;
-            if (lane == 0) t = (int)atomicAdd(scalar_counter, 1u);
-            const WtTile T = ws_tile(P, __shfl_sync(FULL, t, 0), nba, 0);
-            if (T.np == 0) break;
-            const RawLayer &Ly = P.layer[T.layer];
-            float obj1[1], lth1[1];
-            unsigned bits1[1][NW];
-            ldg_stream<1, NW>(P, Ly, T.ba, T.p0 + lane, lane < T.np, obj1, lth1, bits1);
+        // ---------------- emit warp ----------------
+        const int e = warp - WS_STREAM;
+        for (unsigned n = 0u;; ++n) {
+            const int kslot = (int)(n % WS_PK);
+            WsPacket<NW> &K = S.pk[e][kslot];
+            mbar_wait_idle(&S.pk_full[e][kslot], (n / WS_PK) & 1u);
+            if (K.stop) break;                                           // warp-uniform
+#ifndef YL_WS_NOEMIT                                                     // (diagnostic build: the streaming side alone)
+            const int cnt = (int)min(*reinterpret_cast<volatile unsigned *>(&K.n), 0x7FFFFFFFu);
+            if (cnt <= WS_QCAP) {
+                emit_packet<NW>(P, P.layer[K.layer], K, cnt);
+            } else {
+                // dense tile: more flagged pairs than the packet queues; the flag words drive the re-reading form
+                ws_fallback<NW>(P, K, S.em[e]);
+            }
+#endif
             __syncwarp();
-            sobj1[lane] = obj1[0];
-            emit_pairs<1, NW>(P, Ly, T.ba, T.p0, lth1, bits1, E, sobj1);
-            __syncwarp();
+            if (lane == 0) mbar_arrive(&S.pk_empty[e][kslot]);
         }
     }
 }
+
 
 // grid = (sum of tiles over the scales, img_count*3): one launch covers all scales of an image group.
 template <int NW>
@@ -1279,7 +1361,7 @@ static const bool g_split = !g_ws && !(getenv("YL_FILTER") && strcmp(getenv("YL_
 // SM so that CTAs of other kernels can be co-resident (cross-step pipelining experiments, tools/xstep_probe.py).
 static const int g_flag_smem = getenv("YL_FLAG_SMEM") ? atoi(getenv("YL_FLAG_SMEM")) : 0;
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda).
-static int encode_plane_map(CUtensorMap *map, const float *raw, int F2, long rows)
+static int encode_plane_map(CUtensorMap *map, const float *raw, int F2, long rows, int box_rows = WT_KC)
 {
     static PFN_encodeTiled fn = nullptr;
     if (!fn) {
@@ -1290,11 +1372,34 @@ static int encode_plane_map(CUtensorMap *map, const float *raw, int F2, long row
     }
     const cuuint64_t gdim[2] = {(cuuint64_t)F2, (cuuint64_t)rows};
     const cuuint64_t gstr[1] = {(cuuint64_t)F2 * sizeof(float)};
-    const cuuint32_t box[2] = {(cuuint32_t)WT_BOX, (cuuint32_t)WT_KC};
+    const cuuint32_t box[2] = {(cuuint32_t)WT_BOX, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)raw, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? YL_OK : YL_ERR_CUDA_BASE + (int)cudaErrorInvalidValue;
+}
+
+// Side streams of the warp-specialised form: the unaligned scales' flag / emit kernels are forked off the caller's stream
+// and joined again behind the persistent kernel (event record / wait; capturable into a CUDA graph).  One side stream and
+// event pair per (device, caller stream), created on first use and kept for the life of the process.
+struct SideLane { int dev; cudaStream_t user, side; cudaEvent_t fork, join; };
+static std::mutex g_side_mu;
+static std::vector<SideLane> g_side;
+static int side_lane(cudaStream_t user, SideLane *out)
+{
+    int dev = 0;
+    YL_CUDA_TRY(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_side_mu);
+    for (const SideLane &l : g_side)
+        if (l.dev == dev && l.user == user) { *out = l; return YL_OK; }
+    SideLane l;
+    l.dev = dev; l.user = user;
+    YL_CUDA_TRY(cudaStreamCreateWithFlags(&l.side, cudaStreamNonBlocking));
+    YL_CUDA_TRY(cudaEventCreateWithFlags(&l.fork, cudaEventDisableTiming));
+    YL_CUDA_TRY(cudaEventCreateWithFlags(&l.join, cudaEventDisableTiming));
+    g_side.push_back(l);
+    *out = l;
+    return YL_OK;
 }
 
 static int g_num_sms()
@@ -1372,7 +1477,7 @@ static int filter_raw_impl(const float *const *raw, const int *F, int n_layers, 
     for (int pass = 0; pass < 2; ++pass)
         for (int l = 0; l < n_layers; ++l) {
             RawLayer Ly = lay[l];
-            if (n_tma > 0) {                                                 // everything goes through the persistent kernel
+            if (n_tma > 0 && !(g_ws && !Ly.tma)) {                            // goes through the persistent kernel
                 if ((pass == 0) != (Ly.tma == 1)) continue;
                 Ly.tile_boxes = Ly.tma ? WT_BOX : 32;
                 Ly.tiles = (Ly.F2 + Ly.tile_boxes - 1) / Ly.tile_boxes;
@@ -1391,7 +1496,58 @@ static int filter_raw_impl(const float *const *raw, const int *F, int n_layers, 
     cudaStream_t st = (cudaStream_t)stream;
     const int NW = (C + 31) / 32;
     if (NW < 1 || NW > 4) return YL_ERR_CLASSES;
-    if (Pt.n_layers > 0) {
+    // warp-specialised form: the scales the persistent kernel does not take (unaligned planes) are forked onto a side stream
+    // and run next to it through the split kernels; joined below
+    cudaStream_t st_l = st;
+    SideLane lane;
+    bool forked = false;
+    if (g_ws && Pt.n_layers > 0 && Pl.n_layers > 0) {
+        const int rc = side_lane(st, &lane);
+        if (rc != YL_OK) return rc;
+        YL_CUDA_TRY(cudaEventRecord(lane.fork, st));
+        YL_CUDA_TRY(cudaStreamWaitEvent(lane.side, lane.fork, 0));
+        st_l = lane.side;
+        forked = true;
+    }
+    auto launch_ldg = [&]() -> int {
+        if (Pl.n_layers > 0) {
+            dim3 grid(tiles_ldg, img_count * 3);
+            if (g_split || g_ws) {
+                if (stages & 1) {
+                    switch (NW) {
+                    case 1: k_flag_raw<1><<<grid, K1_THREADS, g_flag_smem, st_l>>>(Pl); break;
+                    case 2: k_flag_raw<2><<<grid, K1_THREADS, g_flag_smem, st_l>>>(Pl); break;
+                    case 3: k_flag_raw<3><<<grid, K1_THREADS, g_flag_smem, st_l>>>(Pl); break;
+                    default: k_flag_raw<4><<<grid, K1_THREADS, g_flag_smem, st_l>>>(Pl); break;
+                    }
+                    YL_LAUNCH_CHECK();
+                }
+                if (stages & 2) {
+                    const bool pdl = pdl_enabled() && (stages & 1);             // directly behind k_flag_raw on the stream
+                    cudaError_t le;
+                    switch (NW) {
+                    case 1: le = launch_after(k_emit_flagged<1>, grid, dim3(K1_THREADS), 0, st_l, pdl, Pl); break;
+                    case 2: le = launch_after(k_emit_flagged<2>, grid, dim3(K1_THREADS), 0, st_l, pdl, Pl); break;
+                    case 3: le = launch_after(k_emit_flagged<3>, grid, dim3(K1_THREADS), 0, st_l, pdl, Pl); break;
+                    default: le = launch_after(k_emit_flagged<4>, grid, dim3(K1_THREADS), 0, st_l, pdl, Pl); break;
+                    }
+                    if (le != cudaSuccess) return YL_ERR_CUDA_BASE + (int)le;
+                }
+            } else {
+                switch (NW) {
+                case 1: k_filter_raw<1><<<grid, K1_THREADS, 0, st_l>>>(Pl); break;
+                case 2: k_filter_raw<2><<<grid, K1_THREADS, 0, st_l>>>(Pl); break;
+                case 3: k_filter_raw<3><<<grid, K1_THREADS, 0, st_l>>>(Pl); break;
+                default: k_filter_raw<4><<<grid, K1_THREADS, 0, st_l>>>(Pl); break;
+                }
+            }
+            YL_LAUNCH_CHECK();
+        }
+        return YL_OK;
+    };
+    // forked: the persistent kernel is enqueued first so that its one CTA per SM is placed before the side stream's CTAs
+    if (!forked) { const int rc = launch_ldg(); if (rc != YL_OK) return rc; }
+    if (Pt.n_layers > 0 && (!g_ws || (stages & 1))) {
         const int nba = img_count * 3;
         const int n_tiles = nba * tiles_tma;                                 // warp tiles
         const size_t smem = sizeof(WtSmem);
@@ -1399,7 +1555,6 @@ static int filter_raw_impl(const float *const *raw, const int *F, int n_layers, 
         const int want = (n_tiles + K1_WARPS - 1) / K1_WARPS;
         const int grid = want < ctas_per_sm * g_num_sms() ? want : ctas_per_sm * g_num_sms();
         unsigned *tile_counter = (unsigned *)(w + L.off_tile_count) + img_first;
-        unsigned *scalar_counter = (unsigned *)(w + L.off_tile_count) + B + img_first;
         TmaMaps maps;
         memset(&maps, 0, sizeof(maps));
         for (int l = 0; l < Pt.n_layers; ++l) {
@@ -1426,46 +1581,28 @@ static int filter_raw_impl(const float *const *raw, const int *F, int n_layers, 
         }                                                                                                            \
         const int want_ws = (n_tiles + WS_STREAM - 1) / WS_STREAM;                                                   \
         const int grid_ws = want_ws < g_num_sms() ? want_ws : g_num_sms();                                           \
-        k_filter_raw_ws<NW_><<<grid_ws, WS_THREADS, smem_ws, st>>>(Pt, maps, nba, tile_counter, scalar_counter);      \
+        k_filter_raw_ws<NW_><<<grid_ws, WS_THREADS, smem_ws, st>>>(Pt, wmaps, nba, tile_counter);                     \
     } break;
-        if (g_ws) { switch (NW) { YL_WS_CASE(1) YL_WS_CASE(2) YL_WS_CASE(3) YL_WS_CASE(4) } }
+        if (g_ws) {
+            TmaMapsWs wmaps;
+            memset(&wmaps, 0, sizeof(wmaps));
+            for (int l = 0; l < Pt.n_layers; ++l) {
+                wmaps.cls[l] = maps.m[l];
+                const int rc = encode_plane_map(&wmaps.head[l], Pt.layer[l].raw, Pt.layer[l].F2, (long)B * 3 * (5 + C), WS_HEAD);
+                if (rc != YL_OK) return rc;
+            }
+            switch (NW) { YL_WS_CASE(1) YL_WS_CASE(2) YL_WS_CASE(3) YL_WS_CASE(4) }
+        }
         else switch (NW) { YL_TMA_CASE(1) YL_TMA_CASE(2) YL_TMA_CASE(3) YL_TMA_CASE(4) }
 #undef YL_WS_CASE
 #undef YL_TMA_CASE
         YL_LAUNCH_CHECK();
     }
-    if (Pl.n_layers > 0) {
-        dim3 grid(tiles_ldg, img_count * 3);
-        if (g_split) {
-            if (stages & 1) {
-                switch (NW) {
-                case 1: k_flag_raw<1><<<grid, K1_THREADS, g_flag_smem, st>>>(Pl); break;
-                case 2: k_flag_raw<2><<<grid, K1_THREADS, g_flag_smem, st>>>(Pl); break;
-                case 3: k_flag_raw<3><<<grid, K1_THREADS, g_flag_smem, st>>>(Pl); break;
-                default: k_flag_raw<4><<<grid, K1_THREADS, g_flag_smem, st>>>(Pl); break;
-                }
-                YL_LAUNCH_CHECK();
-            }
-            if (stages & 2) {
-                const bool pdl = pdl_enabled() && (stages & 1);             // directly behind k_flag_raw on the stream
-                cudaError_t le;
-                switch (NW) {
-                case 1: le = launch_after(k_emit_flagged<1>, grid, dim3(K1_THREADS), 0, st, pdl, Pl); break;
-                case 2: le = launch_after(k_emit_flagged<2>, grid, dim3(K1_THREADS), 0, st, pdl, Pl); break;
-                case 3: le = launch_after(k_emit_flagged<3>, grid, dim3(K1_THREADS), 0, st, pdl, Pl); break;
-                default: le = launch_after(k_emit_flagged<4>, grid, dim3(K1_THREADS), 0, st, pdl, Pl); break;
-                }
-                if (le != cudaSuccess) return YL_ERR_CUDA_BASE + (int)le;
-            }
-        } else {
-            switch (NW) {
-            case 1: k_filter_raw<1><<<grid, K1_THREADS, 0, st>>>(Pl); break;
-            case 2: k_filter_raw<2><<<grid, K1_THREADS, 0, st>>>(Pl); break;
-            case 3: k_filter_raw<3><<<grid, K1_THREADS, 0, st>>>(Pl); break;
-            default: k_filter_raw<4><<<grid, K1_THREADS, 0, st>>>(Pl); break;
-            }
-        }
-        YL_LAUNCH_CHECK();
+    if (forked) {
+        const int rc = launch_ldg();
+        if (rc != YL_OK) return rc;
+        YL_CUDA_TRY(cudaEventRecord(lane.join, lane.side));
+        YL_CUDA_TRY(cudaStreamWaitEvent(st, lane.join, 0));
     }
     return YL_OK;
 }

@@ -1,0 +1,279 @@
+// yl_xchg.cu -- the final exchange of the image-sharded path: every rank ends up with the detections of
+// every image, rank r's images at rows [r*B, (r+1)*B).
+//
+// One process per GPU.  Each rank owns ONE device allocation (the "window") that its peers map through CUDA IPC:
+//     rows   [slots][world*B][cap_out][7] fp32     counts [slots][world*B] i32
+//     flag   [slots][world] u32   "source s has delivered epoch e of this slot"      (written by the peers)
+//     ack    [slots][world] u32   "reader s has released epoch e of this slot"       (written by the peers)
+//     epoch  [slots] u32          completed exchanges of the slot                      (local)
+// k_xchg_push copies the kept rows of the local images (exactly counts[b] rows each, 128-bit loads, one store per peer over
+// NVLink: fire-and-forget writes, no collective, no staging) into every window, then publishes flag = epoch + 1 behind a
+// system-scope fence.  k_xchg_wait spins (bounded) until every source's flag reached epoch + 1; k_xchg_release bumps the
+// epoch and tells every peer that this rank is done reading the slot, which is what a peer's next push into that slot
+// waits for (credit: a slot is never overwritten while somebody still reads it).  Nothing here needs a host
+// synchronisation or a changing kernel argument, so push / wait / release are captured into the step's CUDA graph on a
+// side branch and the exchange of step i runs under the kernels of step i+1.
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "yl_common.cuh"
+#include "../../include/yolo_head.h"
+
+namespace yl {
+
+constexpr int XCHG_MAX_WORLD = 16;
+constexpr int XCHG_THREADS = 256;
+
+struct XchgWindow {                  // device pointers into ONE rank's window
+    float *rows;
+    int *counts;
+    unsigned *flag, *ack, *epoch;
+};
+struct XchgPeers {
+    XchgWindow w[XCHG_MAX_WORLD];
+};
+
+struct XchgLayout {
+    size_t off_rows, off_counts, off_flag, off_ack, off_epoch, off_done, off_status, total;
+};
+static XchgLayout xchg_layout(int world, int B, long cap_out, int slots)
+{
+    XchgLayout L;
+    size_t o = 0;
+    L.off_rows = o;   o += align_up(sizeof(float) * 7 * (size_t)slots * world * B * cap_out, 256);
+    L.off_counts = o; o += align_up(sizeof(int) * (size_t)slots * world * B, 256);
+    L.off_flag = o;   o += align_up(sizeof(unsigned) * (size_t)slots * XCHG_MAX_WORLD, 256);
+    L.off_ack = o;    o += align_up(sizeof(unsigned) * (size_t)slots * XCHG_MAX_WORLD, 256);
+    L.off_epoch = o;  o += align_up(sizeof(unsigned) * (size_t)slots, 256);
+    L.off_done = o;   o += align_up(sizeof(unsigned) * (size_t)slots, 256);
+    L.off_status = o; o += 256;
+    L.total = o;
+    return L;
+}
+
+__device__ __forceinline__ unsigned ld_sys(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_sys(unsigned *p, unsigned v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long now_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Spin until *p >= want (wrap-safe), at most limit_ns; returns false on time-out (the caller records it instead of hanging).
+__device__ __forceinline__ bool spin_ge(const unsigned *p, unsigned want, unsigned long long limit_ns)
+{
+    const unsigned long long t0 = now_ns();
+    while ((int)(ld_sys(p) - want) < 0) {
+        __nanosleep(200);
+        if (now_ns() - t0 > limit_ns) return false;
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(XCHG_THREADS)
+k_xchg_push(const __grid_constant__ XchgPeers P, int rank, int world, int B, long cap_out, int slots, int slot,
+            const float *__restrict__ rows, const int *__restrict__ counts, unsigned *__restrict__ done,
+            int *__restrict__ status, unsigned long long limit_ns)
+{
+    __shared__ unsigned sh_epoch;
+    __shared__ int sh_ok;
+    const XchgWindow &me = P.w[rank];
+    if (threadIdx.x == 0) { sh_epoch = me.epoch[slot]; sh_ok = 1; }
+    __syncthreads();
+    const unsigned epoch = sh_epoch;
+    // credit: every reader has released the previous use of this slot (ack >= epoch; epoch counts completed exchanges)
+    if (threadIdx.x < world && !spin_ge(me.ack + slot * XCHG_MAX_WORLD + threadIdx.x, epoch, limit_ns)) sh_ok = 0;
+    __syncthreads();
+    if (!sh_ok) {
+        if (threadIdx.x == 0) atomicExch(status, 1);
+        return;
+    }
+    const size_t img_f4 = (size_t)cap_out * 7 / 4;                   // float4s per image slot (cap_out % 4 == 0)
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        const int n = min(max(counts[b], 0), (int)cap_out);
+        const unsigned nf4 = ((unsigned)n * 7u + 3u) >> 2;           // whole float4s: the padding lies inside the image's own capacity
+        const float4 *src = reinterpret_cast<const float4 *>(rows) + (size_t)b * img_f4;
+        const size_t dst_img = ((size_t)slot * world * B + (size_t)rank * B + b);
+        for (unsigned i = threadIdx.x; i < nf4; i += XCHG_THREADS) {
+            const float4 v = src[i];
+            for (int p = 0; p < world; ++p) reinterpret_cast<float4 *>(P.w[p].rows)[dst_img * img_f4 + i] = v;
+        }
+        if (threadIdx.x < world) P.w[threadIdx.x].counts[dst_img] = n;
+    }
+    // publish: all CTAs' stores are fenced at system scope before the last CTA raises the flags
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        sh_ok = (atomicAdd(done + slot, 1u) == gridDim.x - 1) ? 2 : 1;
+    }
+    __syncthreads();
+    if (sh_ok == 2) {
+        if (threadIdx.x == 0) done[slot] = 0u;
+        __threadfence_system();
+        if (threadIdx.x < world) st_sys(P.w[threadIdx.x].flag + slot * XCHG_MAX_WORLD + rank, epoch + 1u);
+    }
+}
+
+__global__ void k_xchg_wait(const __grid_constant__ XchgPeers P, int rank, int world, int slot, int *__restrict__ status,
+                            unsigned long long limit_ns)
+{
+    const XchgWindow &me = P.w[rank];
+    const unsigned epoch = me.epoch[slot];
+    if (threadIdx.x < world && !spin_ge(me.flag + slot * XCHG_MAX_WORLD + threadIdx.x, epoch + 1u, limit_ns)) atomicExch(status, 2);
+    __threadfence_system();
+}
+
+__global__ void k_xchg_release(const __grid_constant__ XchgPeers P, int rank, int world, int slot)
+{
+    const XchgWindow &me = P.w[rank];
+    __shared__ unsigned sh_epoch;
+    if (threadIdx.x == 0) sh_epoch = me.epoch[slot] + 1u;
+    __syncthreads();
+    if (threadIdx.x < world) st_sys(P.w[threadIdx.x].ack + slot * XCHG_MAX_WORLD + rank, sh_epoch);
+    __syncthreads();
+    if (threadIdx.x == 0) me.epoch[slot] = sh_epoch;
+}
+
+}  // namespace yl
+
+using namespace yl;
+
+struct yl_xchg {
+    int device, rank, world, B, slots, push_ctas;
+    long cap_out;
+    XchgLayout L;
+    char *window;                      // this rank's allocation
+    char *peer[XCHG_MAX_WORLD];        // mapped windows (peer[rank] == window)
+    XchgPeers P;
+    unsigned long long limit_ns;
+    bool connected;
+};
+
+static XchgWindow window_of(char *base, const XchgLayout &L)
+{
+    XchgWindow w;
+    w.rows = (float *)(base + L.off_rows);
+    w.counts = (int *)(base + L.off_counts);
+    w.flag = (unsigned *)(base + L.off_flag);
+    w.ack = (unsigned *)(base + L.off_ack);
+    w.epoch = (unsigned *)(base + L.off_epoch);
+    return w;
+}
+
+extern "C" int yl_xchg_destroy(yl_xchg *x)
+{
+    if (!x) return YL_OK;
+    cudaSetDevice(x->device);
+    for (int p = 0; p < x->world; ++p)
+        if (p != x->rank && x->peer[p]) cudaIpcCloseMemHandle(x->peer[p]);
+    if (x->window) cudaFree(x->window);
+    free(x);
+    return YL_OK;
+}
+
+extern "C" int yl_xchg_create(yl_xchg **out, int device, int rank, int world, int B, long cap_out, int slots)
+{
+    if (!out || rank < 0 || world < 1 || world > XCHG_MAX_WORLD || rank >= world || B <= 0 || cap_out <= 0 || cap_out % 4 != 0 ||
+        slots < 1 || slots > 8)
+        return YL_ERR_ARG;
+    yl_xchg *x = (yl_xchg *)calloc(1, sizeof(yl_xchg));
+    if (!x) return YL_ERR_ARG;
+    x->device = device; x->rank = rank; x->world = world; x->B = B; x->cap_out = cap_out; x->slots = slots;
+    x->L = xchg_layout(world, B, cap_out, slots);
+    x->limit_ns = 5000000000ull;                                     // 5 s: a missing peer is reported, not waited for forever
+    x->push_ctas = getenv("YL_XCHG_CTAS") ? atoi(getenv("YL_XCHG_CTAS")) : 32;
+    if (x->push_ctas < 1) x->push_ctas = 1;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaMalloc(&x->window, x->L.total);
+    // flags, acks, epochs, counters start at zero; the row area needs no initialisation
+    if (e == cudaSuccess) e = cudaMemset(x->window + x->L.off_counts, 0, x->L.total - x->L.off_counts);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { yl_xchg_destroy(x); return YL_ERR_CUDA_BASE + (int)e; }
+    x->peer[rank] = x->window;
+    *out = x;
+    return YL_OK;
+}
+
+extern "C" size_t yl_xchg_handle_bytes(void) { return sizeof(cudaIpcMemHandle_t); }
+
+extern "C" int yl_xchg_local_handle(yl_xchg *x, void *handle)
+{
+    if (!x || !handle) return YL_ERR_ARG;
+    YL_CUDA_TRY(cudaSetDevice(x->device));
+    cudaIpcMemHandle_t h;
+    YL_CUDA_TRY(cudaIpcGetMemHandle(&h, x->window));
+    memcpy(handle, &h, sizeof(h));
+    return YL_OK;
+}
+
+extern "C" int yl_xchg_connect(yl_xchg *x, const void *handles)
+{
+    if (!x || (!handles && x->world > 1)) return YL_ERR_ARG;
+    YL_CUDA_TRY(cudaSetDevice(x->device));
+    for (int p = 0; p < x->world; ++p) {
+        if (p == x->rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char *)handles + (size_t)p * sizeof(h), sizeof(h));
+        void *ptr = nullptr;
+        YL_CUDA_TRY(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        x->peer[p] = (char *)ptr;
+    }
+    for (int p = 0; p < x->world; ++p) x->P.w[p] = window_of(x->peer[p], x->L);
+    x->connected = true;
+    return YL_OK;
+}
+
+extern "C" int yl_xchg_push(yl_xchg *x, const float *rows, const int *counts, int slot, yl_stream_t stream)
+{
+    if (!x || !rows || !counts || slot < 0 || slot >= x->slots || !x->connected) return YL_ERR_ARG;
+    if (((uintptr_t)rows) % 16 != 0) return YL_ERR_ARG;
+    const int grid = x->push_ctas < x->B ? x->push_ctas : x->B;
+    k_xchg_push<<<grid, XCHG_THREADS, 0, (cudaStream_t)stream>>>(x->P, x->rank, x->world, x->B, x->cap_out, x->slots, slot, rows, counts,
+                                                                 (unsigned *)(x->window + x->L.off_done),
+                                                                 (int *)(x->window + x->L.off_status), x->limit_ns);
+    YL_LAUNCH_CHECK();
+    return YL_OK;
+}
+
+extern "C" int yl_xchg_wait(yl_xchg *x, int slot, yl_stream_t stream)
+{
+    if (!x || slot < 0 || slot >= x->slots || !x->connected) return YL_ERR_ARG;
+    k_xchg_wait<<<1, 32, 0, (cudaStream_t)stream>>>(x->P, x->rank, x->world, slot, (int *)(x->window + x->L.off_status), x->limit_ns);
+    YL_LAUNCH_CHECK();
+    return YL_OK;
+}
+
+extern "C" int yl_xchg_release(yl_xchg *x, int slot, yl_stream_t stream)
+{
+    if (!x || slot < 0 || slot >= x->slots || !x->connected) return YL_ERR_ARG;
+    k_xchg_release<<<1, 32, 0, (cudaStream_t)stream>>>(x->P, x->rank, x->world, slot);
+    YL_LAUNCH_CHECK();
+    return YL_OK;
+}
+
+extern "C" void *yl_xchg_rows(yl_xchg *x, int slot)
+{
+    if (!x || slot < 0 || slot >= x->slots) return nullptr;
+    return x->window + x->L.off_rows + sizeof(float) * 7 * (size_t)slot * x->world * x->B * x->cap_out;
+}
+
+extern "C" void *yl_xchg_counts(yl_xchg *x, int slot)
+{
+    if (!x || slot < 0 || slot >= x->slots) return nullptr;
+    return x->window + x->L.off_counts + sizeof(int) * (size_t)slot * x->world * x->B;
+}
+
+extern "C" void *yl_xchg_status(yl_xchg *x)
+{
+    return x ? (void *)(x->window + x->L.off_status) : nullptr;
+}

@@ -10,7 +10,10 @@ def patch_reference(loss_forward=True):
     N4); with False the reference's own forward keeps running on top of the B200 YOLOLayer and build_target -- it
     multiplies dict['output'] by its masks in place (yololoss.py:402-408), which the autograd node of the B200 YOLOLayer
     tolerates because it keeps the raw tensor, not its output.  Returns the list of patched attributes."""
-    from . import yololayer as my_layer, postprocess as my_post, yololoss as my_loss
+    # (not `from . import postprocess`: the package attribute of that name is the function re-exported by __init__)
+    my_layer = importlib.import_module(".yololayer", __package__)
+    my_post = importlib.import_module(".postprocess", __package__)
+    my_loss = importlib.import_module(".yololoss", __package__)
     done = []
     ref_layer = importlib.import_module("yolo.model.yololayer")
     ref_layer.YOLOLayer = my_layer.YOLOLayer

@@ -36,3 +36,102 @@ def allgather_detections(rows, counts, group=None):
         k = int(counts_host[i])
         out.append(recv[i, :k] if k else None)
     return out
+
+
+class DetectionExchange:
+    """The final exchange as part of the device path: kept rows go from the NMS output buffer of every rank
+    straight into every rank's gathered buffer by peer stores over NVLink (yl_xchg_*: one window per rank, mapped by the
+    peers through CUDA IPC), counts stay on the device, nothing synchronises with the host, and the three kernels of an
+    exchange (push / wait / release) are graph-capturable, so the exchange of step i runs under the kernels of step i+1.
+
+        ex = DetectionExchange(B_local, cap_out, device)        # collective: all ranks of `group` (handles are all-gathered)
+        ex.push(rows, counts, slot); ex.wait(slot)               # on the current stream
+        out = ex.results(slot)                                   # lazily built list over ALL world*B images (one D2H of counts)
+        ex.release(slot)                                         # the slot may be pushed into again by every rank
+
+    torch.distributed is used once, for the 64-byte handles; NCCL moves no detection.  world == 1 works (self window)."""
+
+    def __init__(self, b_local, cap_out, device, slots=2, group=None):
+        import ctypes
+
+        import numpy as np
+        from . import _cabi
+        self._cabi, self.L = _cabi, _cabi.lib()
+        self.device = torch.device(device)
+        self.B, self.cap_out, self.slots = int(b_local), int(cap_out), int(slots)
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.h = ctypes.c_void_p()
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        _cabi.check(self.L.yl_xchg_create(ctypes.byref(self.h), dev_index, self.rank, self.world, self.B, self.cap_out, self.slots))
+        nb = int(self.L.yl_xchg_handle_bytes())
+        mine = (ctypes.c_ubyte * nb)()
+        _cabi.check(self.L.yl_xchg_local_handle(self.h, mine))
+        if self.world > 1:
+            local = torch.tensor(list(bytes(mine)), dtype=torch.uint8, device=self.device if dist.get_backend(group) == "nccl" else "cpu")
+            allh = torch.empty((self.world * nb,), dtype=torch.uint8, device=local.device)
+            dist.all_gather_into_tensor(allh, local, group=group)
+            blob = bytes(allh.cpu().numpy().astype(np.uint8).tobytes())
+        else:
+            blob = bytes(mine)
+        buf = (ctypes.c_ubyte * len(blob)).from_buffer_copy(blob)
+        _cabi.check(self.L.yl_xchg_connect(self.h, buf))
+        if self.world > 1:
+            dist.barrier(group=group)                      # every window is mapped before anybody pushes
+        self._views = {}
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def push(self, rows, counts, slot):
+        if rows.dtype != torch.float32 or not rows.is_cuda or not rows.is_contiguous() or tuple(rows.shape) != (self.B, self.cap_out, 7):
+            raise ValueError("rows must be a contiguous float32 CUDA tensor [B, cap_out, 7]")
+        if counts.dtype != torch.int32 or not counts.is_cuda or counts.numel() < self.B:
+            raise ValueError("counts must be an int32 CUDA tensor with at least B entries")
+        self._cabi.check(self.L.yl_xchg_push(self.h, rows.data_ptr(), counts.data_ptr(), int(slot), self._stream()))
+
+    def wait(self, slot):
+        self._cabi.check(self.L.yl_xchg_wait(self.h, int(slot), self._stream()))
+
+    def release(self, slot):
+        self._cabi.check(self.L.yl_xchg_release(self.h, int(slot), self._stream()))
+
+    def _view(self, ptr, shape, dtype):
+        """A torch view of library-owned device memory (no copy) through the CUDA array interface."""
+        n = 1
+        for s in shape:
+            n *= s
+
+        class _Mem:
+            pass
+        m = _Mem()
+        m.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4" if dtype == torch.float32 else "<i4",
+                                      "data": (int(ptr), False), "version": 2}
+        return torch.as_tensor(m, device=self.device)
+
+    def gathered(self, slot):
+        """(rows [world*B, cap_out, 7], counts [world*B]) device views of this rank's gathered buffers of a slot."""
+        if slot not in self._views:
+            n = self.world * self.B
+            self._views[slot] = (self._view(self.L.yl_xchg_rows(self.h, int(slot)), (n, self.cap_out, 7), torch.float32),
+                                 self._view(self.L.yl_xchg_counts(self.h, int(slot)), (n,), torch.int32))
+        return self._views[slot]
+
+    def status(self):
+        """0 ok; 1 / 2: a push / wait gave up after its time limit (a rank is missing or stuck).  Synchronises."""
+        return int(self._view(self.L.yl_xchg_status(self.h), (1,), torch.int32).cpu()[0])
+
+    def results(self, slot):
+        """List over all world*B images (rank-major) of [K_i, 7] device views / None, built from the gathered buffers (one D2H
+        of the counts).  Call after wait(slot) has been enqueued; the views are valid until release(slot)."""
+        rows, counts = self.gathered(slot)
+        ch = counts.cpu()
+        if self.status() != 0:
+            raise RuntimeError("detection exchange timed out (status %d)" % self.status())
+        return [rows[i, :int(ch[i])] if int(ch[i]) else None for i in range(rows.shape[0])]
+
+    def close(self):
+        if self.h:
+            self._views = {}
+            self._cabi.check(self.L.yl_xchg_destroy(self.h))
+            self.h = None
