@@ -151,6 +151,12 @@ int yl_build_target(const float *pred, const long *pred_strides, const float *la
  * --------------------------------------------------------------------------------------------------------- */
 int yl_coco_rows(const float *rows, const int *row_image, long K, const double *img_info, const long long *image_ids,
                  const int *class_ids, int n_classes, int mode, double *out, yl_stream_t stream);
+/* The same epilogue straight on the padded device output of yl_nms (rows [B, cap_out, 7] + counts [B] = meta[0..B)): one launch
+ * for the whole batch, no concatenation and no per-image index tensor; out is compact, [sum counts, 7], image b's rows at the
+ * exclusive prefix of the counts. */
+int yl_coco_rows_padded(const float *rows, const int *counts, int B, long cap_out, const double *img_info,
+                        const long long *image_ids, const int *class_ids, int n_classes, int mode, double *out,
+                        yl_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * N2  YOLOLoss.forward for one layer, fused            replaces yolo/model/yololoss.py:390-432

@@ -84,5 +84,8 @@ def test_bench_reference_arm_prints_exactly_one_json_line():
     assert len(lines) == 1, p.stdout[:2000]
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "images/s" and d["higher_is_better"] is True
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    # the unmodified reference when it is installed under baseline/_ref (tools/install_reference.sh), else the oracle's C port
+    have_ref = os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "yolo"))
+    assert d["cpu_baseline"]["kind"] == ("reference" if have_ref else "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline_port"]["kind"] == "port" and d["cpu_baseline_port"]["value"] > 0
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]

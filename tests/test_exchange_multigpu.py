@@ -17,13 +17,14 @@ pytestmark = pytest.mark.gpu
 
 B, IMG, C, CONF, NMS = 4, 416, 80, 1e-3, 0.4
 STEPS = 5
+CAP = 32768
 
 
 def _detect(seed, dev):
     import yolov4_b200 as yb
     from yolov4_b200.synth import synth_head_outputs
     raws = synth_head_outputs(B, IMG, C, seed=seed, device=dev, fg_prob=0.02, clustered=True)
-    hp = yb.HeadPostprocessor(B, [IMG // 8, IMG // 16, IMG // 32], C, CONF, NMS, device=dev, cap_out=4096)
+    hp = yb.HeadPostprocessor(B, [IMG // 8, IMG // 16, IMG // 32], C, CONF, NMS, device=dev, cap_out=CAP)
     rows, meta = hp.run(raws)
     torch.cuda.synchronize(dev)
     return hp, rows, meta
@@ -38,8 +39,8 @@ def _worker(rank, world, port, q):
         if world > 1:
             dist.init_process_group("gloo", rank=rank, world_size=world)
         from yolov4_b200.sharded import DetectionExchange
-        ex = DetectionExchange(B, 4096, dev, slots=2)
-        ok, n_rows = True, 0
+        ex = DetectionExchange(B, CAP, dev, slots=2)
+        ok, n_rows, first_bad = True, 0, ""
         for step in range(STEPS):
             slot = step % 2
             hp, rows, meta = _detect(1000 * step + rank, dev)
@@ -56,19 +57,26 @@ def _worker(rank, world, port, q):
                     g = got[r * B + b]
                     k = int(cnt[b])
                     if k == 0:
-                        ok = ok and g is None
+                        good = g is None
                     else:
-                        ok = ok and g is not None and g.shape[0] == k and \
+                        good = g is not None and g.shape[0] == k and \
                             np.array_equal(g.cpu().numpy().view(np.uint32), rr[b, :k].cpu().numpy().view(np.uint32))
                         n_rows += k
+                    if not good and ok:
+                        first_bad = "step %d slot %d source rank %d image %d: want %d rows, got %s" % (
+                            step, slot, r, b, k, None if g is None else tuple(g.shape))
+                    ok = ok and good
             ex.release(slot)
         torch.cuda.synchronize(dev)
-        ok = ok and ex.status() == 0 and n_rows > 100
+        st_ = ex.status()
+        if st_ != 0 or n_rows <= 100:
+            first_bad += " status %d n_rows %d" % (st_, n_rows)
+        ok = ok and st_ == 0 and n_rows > 100
         ex.close()
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
-        q.put((rank, bool(ok), n_rows))
+        q.put((rank, bool(ok), n_rows, first_bad, ))
     except Exception as e:                                        # pragma: no cover
         q.put((rank, False, repr(e)))
 

@@ -20,4 +20,4 @@ for r in rows[-7:]:
 PY
 YL_FILTER=ws N=2 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_filter_raw_ws -s 2 -c 1 -o gpurun_out/ws_full python tools/step_probe.py > gpurun_out/ws_ncu.log 2>&1
 tail -2 gpurun_out/ws_ncu.log
-timeout 600 python -m pytest tests/test_exchange_multigpu.py -m gpu -x -q 2>&1 | tail -5
+timeout 600 python -m pytest tests/test_exchange_multigpu.py -m gpu -x -q 2>&1 | tail -30

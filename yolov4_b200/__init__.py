@@ -12,7 +12,7 @@ from .postprocess import postprocess, detect_raw, HeadPostprocessor, ANCHORS_PX,
 from .yololayer import YOLOLayer, decode_dense_cat  # noqa: F401
 from .yololoss import YOLOLoss, build_target, fused_yolo_loss, fused_yolo_loss_components  # noqa: F401
 from .patch import patch_reference  # noqa: F401
-from .epilogue import coco_rows, coco_dicts, detect_rows  # noqa: F401
+from .epilogue import coco_rows, coco_dicts, detect_rows, coco_rows_padded  # noqa: F401
 
 __all__ = ["postprocess", "detect_raw", "HeadPostprocessor", "YOLOLayer", "decode_dense_cat", "YOLOLoss", "build_target", "fused_yolo_loss", "fused_yolo_loss_components", "patch_reference", "coco_rows", "coco_dicts", "detect_rows",
            "ANCHORS_PX", "ANCHOR_MASK"]

@@ -928,26 +928,6 @@ __device__ __forceinline__ void emit_packet(const RawParams &P, const RawLayer &
     }
 }
 
-// Queue this lane's flagged (box slot, class, logit) entries of one chunk; sp = the lane's first box in the stage.
-// Not inlined: the streaming loop stays small, and only the lanes that flagged something come here.
-__device__ __noinline__ void ws_capture(unsigned *n, unsigned short *ent, float *val, const float *sp,
-                                        unsigned a0, unsigned a1, unsigned a2, unsigned a3, int slot0, int cls0)
-{
-#pragma unroll 1
-    for (int v = 0; v < 4; ++v) {
-        unsigned m = (v == 0) ? a0 : ((v == 1) ? a1 : ((v == 2) ? a2 : a3));
-        while (m) {
-            const int k = __ffs(m) - 1;
-            m &= m - 1u;
-            const unsigned q = atomicAdd(n, 1u);
-            if (q < (unsigned)WS_QCAP) {
-                ent[q] = (unsigned short)(((slot0 + v) << 8) | (cls0 + k));
-                val[q] = sp[k * WT_BOX + v];
-            }
-        }
-    }
-}
-
 // Overflow path of an emit warp (cold): the packet's flag words through the re-reading form of the exact pass.
 template <int NW>
 __device__ __noinline__ void ws_fallback(const RawParams &P, WsPacket<NW> &K, EmitWarp &E)
@@ -1021,7 +1001,6 @@ k_filter_raw_ws(const __grid_constant__ RawParams P, const __grid_constant__ Tma
             WsPacket<NW> &K = S.pk[warp][kslot];
             if (!have_pk) {
                 mbar_wait(&S.pk_empty[warp][kslot], ((n_sent / WS_PK) & 1u) ^ 1u);      // first use: passes on the fresh barrier
-                if (lane == 0) K.n = 0u;
                 have_pk = true;
             }
             const bool inb = lane * 4 < cur.np;
@@ -1042,11 +1021,12 @@ k_filter_raw_ws(const __grid_constant__ RawParams P, const __grid_constant__ Tma
                     lth[v] = inb ? class_logit_bound(obj[v], P.thr) : kInf;
                 }
             }
-            __syncwarp();                                              // K.n = 0 is visible; the head slot has been read
+            __syncwarp();                                              // the head slot has been read
             // One flat loop over the class chunks (not unrolled over the flag words: the kernel must stay inside the instruction
             // cache, its two roles run different code on the same SM); a finished flag word goes straight into the packet.
             constexpr int CPW = 32 / WT_KC;                              // chunks per flag word
             unsigned m0 = 0u, m1 = 0u, m2 = 0u, m3 = 0u;
+            unsigned n_queued = 0u;                                      // entries queued for this tile (warp-uniform)
 #pragma unroll 1
             for (int c = 0; c < n_cc; ++c) {
                 mbar_wait(&W.full[s], (ph >> s) & 1u);
@@ -1080,8 +1060,33 @@ k_filter_raw_ws(const __grid_constant__ RawParams P, const __grid_constant__ Tma
                 if (lth[1] == kInf) a1 = 0u;
                 if (lth[2] == kInf) a2 = 0u;
                 if (lth[3] == kInf) a3 = 0u;
-                // rare (~0.6 % of the logits): queue (box slot, class, logit) while the logit is still in the stage
-                if (a0 | a1 | a2 | a3) ws_capture(&K.n, K.ent, K.val, sp, a0, a1, a2, a3, lane * 4, c * WT_KC);
+                // rare (~0.6 % of the logits): queue (box slot, class, logit) while the logit is still in the stage.  Warp-
+                // cooperative: one prefix sum gives every lane its run of queue slots; the running count lives in a register
+                // (no shared-memory atomics, no per-lane loops over four words).
+                {
+                    static_assert(WT_KC == 8, "the four 8-bit chunk masks of a lane are packed into one word");
+                    unsigned am = a0 | (a1 << 8) | (a2 << 16) | (a3 << 24);
+                    if (__ballot_sync(FULL, am != 0u)) {                 // warp-uniform
+                        const int cnt = __popc(am);
+                        int incl = cnt;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const int t = __shfl_up_sync(FULL, incl, o);
+                            if (lane >= o) incl += t;
+                        }
+                        unsigned q = n_queued + (unsigned)(incl - cnt);
+                        n_queued += (unsigned)__shfl_sync(FULL, incl, 31);
+                        while (am) {
+                            const int bit = __ffs(am) - 1;
+                            am &= am - 1u;
+                            if (q < (unsigned)WS_QCAP) {
+                                K.ent[q] = (unsigned short)(((lane * 4 + (bit >> 3)) << 8) | (c * WT_KC + (bit & 7)));
+                                K.val[q] = sp[(bit & 7) * WT_BOX + (bit >> 3)];
+                            }
+                            ++q;
+                        }
+                    }
+                }
                 const int sh = (c % CPW) * WT_KC;
                 m0 |= a0 << sh; m1 |= a1 << sh; m2 |= a2 << sh; m3 |= a3 << sh;
                 __syncwarp();                                            // every lane has read the stage
@@ -1099,12 +1104,12 @@ k_filter_raw_ws(const __grid_constant__ RawParams P, const __grid_constant__ Tma
             }
             __syncwarp();
             // hand the tile over (the loop's last __syncwarp made every lane's queue entries and K.n visible)
-            if (*reinterpret_cast<volatile unsigned *>(&K.n) != 0u) {    // warp-uniform
+            if (n_queued != 0u) {                                        // warp-uniform
                 *reinterpret_cast<float4 *>(&K.sobj[lane * 4]) = make_float4(obj[0], obj[1], obj[2], obj[3]);
 #pragma unroll
                 for (int v = 0; v < 4; ++v) K.box[lane * 4 + v] = braw[v];
                 if (lane < 4) { K.any[lane] = 0u; K.nan[lane] = 0u; }
-                if (lane == 0) { K.layer = cur.layer; K.ba = cur.ba; K.p0 = cur.p0; K.stop = 0; }
+                if (lane == 0) { K.n = n_queued; K.layer = cur.layer; K.ba = cur.ba; K.p0 = cur.p0; K.stop = 0; }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&S.pk_full[warp][kslot]);
                 ++n_sent;

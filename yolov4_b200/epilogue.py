@@ -44,3 +44,26 @@ def coco_dicts(outputs, img_infos, image_ids, class_ids):
 def detect_rows(outputs, img_infos, class_ids):
     """Returns float64 [sum K_i, 7] = (image index, category_id, y1, x1, y2, x2, cls_conf) as detect.parse_info computes them."""
     return _run(outputs, img_infos, list(range(len(outputs))), class_ids, 1)
+
+
+def coco_rows_padded(rows, counts, img_infos, image_ids, class_ids, mode=0, total=None):
+    """The same rows from the padded device output of the fixed-shape path (HeadPostprocessor.run: rows [B, cap_out, 7], counts =
+    meta[:B]) with ONE launch for the whole batch -- no torch.cat, no per-image index tensor.  `total` = sum of the counts when the
+    caller already knows it (HeadPostprocessor.results() has read them); otherwise one D2H read here.
+    mode 0: validate()'s COCO rows, mode 1: detect.parse_info()'s rows."""
+    if not rows.is_cuda or rows.dtype != torch.float32 or rows.dim() != 3 or rows.shape[2] != 7 or not rows.is_contiguous():
+        raise TypeError("rows must be a contiguous float32 CUDA tensor [B, cap_out, 7]; there is no CPU fallback")
+    B, cap_out = int(rows.shape[0]), int(rows.shape[1])
+    dev = rows.device
+    counts = counts[:B].to(device=dev, dtype=torch.int32).contiguous()
+    if total is None:
+        total = int(counts.clamp(0, cap_out).sum())
+    info = torch.tensor([[float(v) for v in inf[:4]] for inf in img_infos], dtype=torch.float64, device=dev)
+    ids = torch.tensor([int(v) for v in image_ids], dtype=torch.int64, device=dev)
+    cids = torch.tensor([int(v) for v in class_ids], dtype=torch.int32, device=dev)
+    out = torch.empty((total, 7), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _cabi.check(_cabi.lib().yl_coco_rows_padded(rows.data_ptr(), counts.data_ptr(), B, cap_out, info.data_ptr(), ids.data_ptr(),
+                                                    cids.data_ptr(), len(class_ids), int(mode), out.data_ptr(),
+                                                    torch.cuda.current_stream().cuda_stream))
+    return out
