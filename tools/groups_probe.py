@@ -13,9 +13,11 @@ def timeit(hp, n=100):
     for _ in range(n): hp.replay()
     ev1.record(); torch.cuda.synchronize()
     return ev0.elapsed_time(ev1) * 1e3 / n
-for mode in ("nms_side", "emit_side"):
+MODES = os.environ.get("MODES", "nms_side,emit_side,pipe3").split(",")
+GROUPS = [int(g) for g in os.environ.get("GROUPS", "1,2,4,8").split(",")]
+for mode in MODES:
     for prio in (0, -1):
-        for G in (1, 2, 4, 8, 16):
+        for G in GROUPS:
             hp = yb.HeadPostprocessor(B, [76, 38, 19], 80, 1e-4, 0.4, n_groups=G, side_priority=prio, mode=mode).capture(raws)
             t = timeit(hp)
             print("mode %-9s prio %2d groups %2d: %.1f us/step %.0f img/s" % (mode, prio, G, t, B / t * 1e6), flush=True)

@@ -12,9 +12,6 @@
 #include <stdlib.h>
 #include <string.h>
 
-#include <mutex>
-#include <vector>
-
 #include "yl_common.cuh"
 #include "../../include/yolo_head.h"
 
@@ -760,89 +757,45 @@ k_filter_raw_tma(const __grid_constant__ RawParams P, const __grid_constant__ Tm
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Warp-specialised form (YL_FILTER=ws): ONE persistent kernel, one CTA per SM, two kinds of warps that never wait for each
-// other's memory latency:
-//   * streaming warps   private TMA rings ([WT_KC class planes x 128 boxes] per stage, UTMALDG.2D + transaction
-//                       mbarriers) as above, plus a [5 planes x 128 boxes] box of tx,ty,tw,th,objectness per tile.  A class
-//                       logit that passes the conservative bound is copied out of the ring stage while it is on-chip
-//                       (box slot, class, logit) into the tile's packet; at the end of the tile the packet also gets
-//                       sigmoid(objectness) and the raw tx,ty,tw,th of the tile's boxes from registers and is handed over.
-//                       The ring never drains while somebody follows the dependent round trips of the exact pass.
-//   * emit warps        one per streaming warp, WS_PK packets in flight: exact spec-math test of the queued pairs, NaN rule,
-//                       one decode per surviving box, slot atomics, 32-byte records.  No global load at all: nothing the
-//                       stream brought on-chip is fetched a second time (k_emit_flagged reads 133 MB of scattered sectors).
-//                       A tile with more queued pairs than the packet holds (dense inputs) falls back to the flag-word
-//                       form of emit_pairs, which re-reads the logits.
-// The scales whose planes are not 16-byte aligned (19x19: 4.8 % of the bytes) cannot be fetched by TMA; they go through
-// k_flag_raw + k_emit_flagged on a forked side stream and run next to this kernel.
+// TMA form of the streaming FLAG pass (YL_FLAG=tma): the same output as k_flag_raw (flag words + sigmoid(objectness), 16 B per
+// box, for k_emit_flagged), produced by ONE persistent CTA per SM that needs a quarter of the register file:
+//   * streaming warps   private TMA rings ([WT_KC class planes x 128 boxes] per stage, UTMALDG.2D + transaction mbarriers,
+//                       objectness plane by a 1-D bulk copy): the bytes in flight live in shared memory, not in registers
+//                       (k_flag_raw keeps 8 CTAs x 128 threads x 64 registers busy to have 128 KB in flight per SM);
+//   * scalar warps      the scales whose planes are not 16-byte aligned (19x19: 4.8 % of the bytes), register-staged loads.
+// What it buys is not its own speed (both forms run at the HBM roofline) but ROOM: with 384 threads x <= 64 registers resident,
+// the emit / NMS CTAs of the previous image group fit next to it, so the chain's latency-bound kernels run UNDER the stream
+// instead of after it (HeadPostprocessor, n_groups > 1).
 // ---------------------------------------------------------------------------------------------------------------
-#ifndef YL_WS_STREAM
-#define YL_WS_STREAM 6
+#ifndef YL_FT_STREAM
+#define YL_FT_STREAM 8
 #endif
-#ifndef YL_WS_PK
-#define YL_WS_PK 2
+#ifndef YL_FT_SCALAR
+#define YL_FT_SCALAR 4
 #endif
-#ifndef YL_WS_STAGES
-#define YL_WS_STAGES 3
+#ifndef YL_FT_STAGES
+#define YL_FT_STAGES 4
 #endif
-#ifndef YL_WS_MAXREG
-#define YL_WS_MAXREG 96                        // register cap: one CTA per SM must leave room for the side stream's CTAs
+#ifndef YL_FT_MAXREG
+#define YL_FT_MAXREG 64
 #endif
-#ifndef YL_WS_SLEEP
-#define YL_WS_SLEEP 100
-#endif
-constexpr int WS_STREAM = YL_WS_STREAM;        // streaming warps per CTA (= emit warps)
-constexpr int WS_PK = YL_WS_PK;                // packets per streaming warp
-constexpr int WS_STAGES = YL_WS_STAGES;        // ring stages per streaming warp (4 KB each)
-constexpr int WS_THREADS = 32 * 2 * WS_STREAM;
-constexpr int WS_QCAP = 256;                   // queued (box slot, class, logit) entries per packet
-constexpr int WS_HEAD = 5;                     // planes of the per-tile head box: tx, ty, tw, th, objectness
+constexpr int FT_STREAM = YL_FT_STREAM;        // streaming warps per CTA
+constexpr int FT_SCALAR = YL_FT_SCALAR;        // scalar warps per CTA
+constexpr int FT_STAGES = YL_FT_STAGES;        // ring stages per streaming warp (4 KB each)
+constexpr int FT_THREADS = 32 * (FT_STREAM + FT_SCALAR);
 
-template <int NW>
-struct alignas(16) WsPacket {
-    float4 box[WT_BOX];                        // raw (tx,ty,tw,th) per box slot; the emit warp decodes surviving boxes in place
-    float sobj[WT_BOX];                        // sigmoid(objectness) per box slot
-    float val[WS_QCAP];                        // queued class logits; sigmoid(logit) of the passing ones after the exact test
-    unsigned bits[NW][WT_BOX];                 // flagged-class words per box slot (overflow fallback)
-    unsigned short ent[WS_QCAP];               // bit15 pass | box slot (7b) << 8 | class (7b)
-    unsigned any[4], nan[4];                   // per box slot: has a surviving pair / has a NaN class logit
-    unsigned n;                                // queued entries (may exceed WS_QCAP: then the fallback path runs)
-    int layer, ba, p0, stop;
+struct alignas(128) FtStream {
+    float stage[FT_STAGES][WT_KC][WT_BOX];
+    float objp[2][WT_BOX];                     // objectness plane of the current / the next tile
+    unsigned long long full[FT_STAGES], obj_full[2];
 };
-struct alignas(128) WsStream {
-    float stage[WS_STAGES][WT_KC][WT_BOX];
-    float head[2][WS_HEAD][WT_BOX];            // tx,ty,tw,th,obj planes of the current / the next tile
-    unsigned long long full[WS_STAGES], head_full[2];
+struct FtSmem {
+    FtStream s[FT_STREAM];
 };
-template <int NW>
-struct WsSmem {
-    WsStream s[WS_STREAM];
-    WsPacket<NW> pk[WS_STREAM][WS_PK];
-    EmitWarp em[WS_STREAM];                    // scratch of the overflow fallback
-    unsigned long long pk_full[WS_STREAM][WS_PK], pk_empty[WS_STREAM][WS_PK];
-};
-struct TmaMapsWs { CUtensorMap cls[3], head[3]; };
-static_assert(sizeof(WsSmem<4>) <= 227 * 1024, "the warp-specialised CTA must fit one SM's shared memory");
-
-// Wait of a warp that has nothing else to do (emit warps between packets): back off between polls so that the spinning
-// does not take issue slots from the streaming warps of the same scheduler.
-__device__ __forceinline__ void mbar_wait_idle(unsigned long long *bar, unsigned parity)
-{
-    unsigned ok;
-    for (;;) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-        if (ok) break;
-        if (YL_WS_SLEEP > 0) __nanosleep(YL_WS_SLEEP);
-    }
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
+static_assert(sizeof(FtSmem) <= 200 * 1024, "the flag CTA must leave shared memory for co-resident emit / NMS CTAs");
 
 // t-th tile among the scales with layer.tma == tma (layer[l].tiles = warp tiles per (image, anchor)); np == 0: no such tile.
-__device__ __forceinline__ WtTile ws_tile(const RawParams &P, int t, int nba, int tma)
+__device__ __forceinline__ WtTile ft_tile(const RawParams &P, int t, int nba, int tma)
 {
     WtTile T;
     T.np = 0; T.src = nullptr; T.layer = 0; T.ba = 0; T.p0 = 0; T.row0 = 0; T.tma = tma;
@@ -864,156 +817,67 @@ __device__ __forceinline__ WtTile ws_tile(const RawParams &P, int t, int nba, in
     return T;
 }
 
-// Exact pass over a packet whose pairs were queued with their logits: no global load.
 template <int NW>
-__device__ __forceinline__ void emit_packet(const RawParams &P, const RawLayer &Ly, WsPacket<NW> &K, int n)
+__global__ void __maxnreg__(YL_FT_MAXREG)
+k_flag_tma(const __grid_constant__ RawParams P, const __grid_constant__ TmaMaps maps, int nba,
+           unsigned *__restrict__ tile_counter, unsigned *__restrict__ scalar_counter)
 {
-    const int lane = threadIdx.x & 31;
-    const int C = P.C;
-    const float thr = P.thr;
-    const int b = K.ba / 3, a = K.ba - 3 * b;
-    const int row_base = Ly.row_off + a * Ly.F2 + K.p0;                // + box slot = row inside the image
-    for (int q = lane; q < n; q += 32) {
-        const unsigned en = K.ent[q];
-        const float t = K.val[q];
-        const int bs = en >> 8;
-        // a NaN class logit makes torch.max (utils.py:139) NaN and drops the whole row (:145)
-        if (t != t) atomicOr(&K.nan[bs >> 5], 1u << (bs & 31));
-        const float cls = spec_sigmoidf(t);
-        if (__fmul_rn(K.sobj[bs], cls) >= thr) {                        // utils.py:170
-            atomicOr(&K.any[bs >> 5], 1u << (bs & 31));
-            K.val[q] = cls;
-            K.ent[q] = (unsigned short)(en | 0x8000u);
-        }
-    }
-    __syncwarp();
-#pragma unroll 1
-    for (int j = 0; j < 4; ++j) {                                        // one decode per surviving box (yololayer.py:150-162)
-        const int bs = 32 * j + lane;
-        if (((K.any[j] & ~K.nan[j]) >> lane) & 1u) {
-            const float4 r = K.box[bs];
-            K.box[bs] = decode_box_v(r.x, r.y, r.z, r.w, Ly.Fw, K.p0 + bs, Ly.aw[a], Ly.ah[a], Ly.stride);
-        }
-    }
-    __syncwarp();
-    for (int q0 = 0; q0 < n; q0 += 128) {
-        unsigned slot[4], en[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {                                    // the slot atomics of four entries are in flight together
-            const int q = q0 + 32 * u + lane;
-            en[u] = 0u;
-            slot[u] = 0xFFFFFFFFu;
-            if (q < n) {
-                en[u] = K.ent[q];
-                const int bs = (en[u] >> 8) & 0x7F;
-                if ((en[u] & 0x8000u) && !((K.nan[bs >> 5] >> (bs & 31)) & 1u))
-                    slot[u] = atomicAdd(&P.seg_count[(unsigned)(b * C + (int)(en[u] & 0x7F))], 1u);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            if (slot[u] < (unsigned)P.cap_seg) {
-                const int q = q0 + 32 * u + lane;
-                const int bs = (en[u] >> 8) & 0x7F;
-                const float cls = K.val[q];
-                const float so = K.sobj[bs];
-                const float s = __fadd_rn(__fmul_rn(so, cls), 0.0f);       // +0 canonicalises -0
-                const unsigned seg = (unsigned)(b * C + (int)(en[u] & 0x7F));
-                uint4 *r = P.cand + ((size_t)seg * P.cap_seg + slot[u]) * 2;
-                const float4 bx = K.box[bs];
-                r[0] = make_uint4(__float_as_uint(s), (unsigned)(row_base + bs), __float_as_uint(cls), __float_as_uint(so));
-                r[1] = make_uint4(__float_as_uint(bx.x), __float_as_uint(bx.y), __float_as_uint(bx.z), __float_as_uint(bx.w));
-            }
-        }
-    }
-}
-
-// Overflow path of an emit warp (cold): the packet's flag words through the re-reading form of the exact pass.
-template <int NW>
-__device__ __noinline__ void ws_fallback(const RawParams &P, WsPacket<NW> &K, EmitWarp &E)
-{
-    const int lane = threadIdx.x & 31;
-    float lth[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-    unsigned bits[4][NW];
-#pragma unroll
-    for (int w = 0; w < NW; ++w) {
-        const uint4 m = *reinterpret_cast<const uint4 *>(&K.bits[w][lane * 4]);
-        bits[0][w] = m.x; bits[1][w] = m.y; bits[2][w] = m.z; bits[3][w] = m.w;
-    }
-    emit_pairs<4, NW>(P, P.layer[K.layer], K.ba, K.p0, lth, bits, E, K.sobj);
-}
-
-template <int NW>
-__global__ void __maxnreg__(YL_WS_MAXREG)
-k_filter_raw_ws(const __grid_constant__ RawParams P, const __grid_constant__ TmaMapsWs maps, int nba,
-                unsigned *__restrict__ tile_counter)
-{
-    extern __shared__ __align__(128) unsigned char ws_smem_raw[];
-    WsSmem<NW> &S = *reinterpret_cast<WsSmem<NW> *>(ws_smem_raw);
+    extern __shared__ __align__(128) unsigned char ft_smem_raw[];
+    FtSmem &S = *reinterpret_cast<FtSmem *>(ft_smem_raw);
     const unsigned FULL = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int C = P.C;
 
     if (threadIdx.x == 0) {
-        for (int w = 0; w < WS_STREAM; ++w) {
-            for (int s = 0; s < WS_STAGES; ++s) mbar_init(&S.s[w].full[s], 1);
-            mbar_init(&S.s[w].head_full[0], 1);
-            mbar_init(&S.s[w].head_full[1], 1);
-            for (int k = 0; k < WS_PK; ++k) { mbar_init(&S.pk_full[w][k], 1); mbar_init(&S.pk_empty[w][k], 1); }
+        for (int w = 0; w < FT_STREAM; ++w) {
+            for (int s = 0; s < FT_STAGES; ++s) mbar_init(&S.s[w].full[s], 1);
+            mbar_init(&S.s[w].obj_full[0], 1);
+            mbar_init(&S.s[w].obj_full[1], 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     pdl_trigger();
+    if (P.reset_words > 0) {
+        // yl_post_reset folded into this kernel (nothing reads the counters before the emit kernel, which waits for this grid);
+        // the two tile counters this kernel itself draws from are NOT among the words it zeroes (see the host code)
+        for (int i = blockIdx.x * FT_THREADS + threadIdx.x; i < P.reset_words; i += gridDim.x * FT_THREADS) P.reset[i] = 0u;
+    }
 
-    if (warp < WS_STREAM) {
+    if (warp < FT_STREAM) {
         // ---------------- streaming warp ----------------
-        WsStream &W = S.s[warp];
-        const int n_cc = (C + WT_KC - 1) / WT_KC;                    // class chunks per tile (>= WS_STAGES, host-checked)
+        FtStream &W = S.s[warp];
+        const int n_cc = (C + WT_KC - 1) / WT_KC;                    // class chunks per tile (>= FT_STAGES, host-checked)
         auto issue_chunk = [&](const WtTile &T, int c, int s) {
             mbar_expect_tx(&W.full[s], WT_KC * WT_BOX * 4u);         // full box, zero fill included
-            tma_load_2d(&W.stage[s][0][0], &maps.cls[T.layer], T.p0, T.row0 + c * WT_KC, &W.full[s]);
+            tma_load_2d(&W.stage[s][0][0], &maps.m[T.layer], T.p0, T.row0 + c * WT_KC, &W.full[s]);
         };
-        auto issue_head = [&](const WtTile &T, int slot) {
-            mbar_expect_tx(&W.head_full[slot], WS_HEAD * WT_BOX * 4u);
-            tma_load_2d(&W.head[slot][0][0], &maps.head[T.layer], T.p0, T.row0 - 5, &W.head_full[slot]);
+        auto issue_obj = [&](const WtTile &T, int slot) {
+            const unsigned bytes = (unsigned)T.np * 4u;
+            mbar_expect_tx(&W.obj_full[slot], bytes);
+            bulk_g2s(&W.objp[slot][0], T.src + 4 * (size_t)P.layer[T.layer].F2, bytes, &W.obj_full[slot]);
         };
-        // the tile counter's round trip is taken one tile ahead: `ahead` is the ticket of the tile after `nxt`, drawn at
-        // the top of an iteration and first used at its bottom
+        // the tile counter's round trip is taken one tile ahead: `ahead` is the ticket of the tile after `nxt`
         auto draw = [&]() { int t = 0; if (lane == 0) t = (int)atomicAdd(tile_counter, 1u); return t; };
-        auto resolve = [&](int t) { return ws_tile(P, __shfl_sync(FULL, t, 0), nba, 1); };
+        auto resolve = [&](int t) { return ft_tile(P, __shfl_sync(FULL, t, 0), nba, 1); };
         WtTile cur = resolve(draw());
         WtTile nxt = cur;
         if (cur.np != 0) nxt = resolve(draw());
         if (lane == 0 && cur.np != 0) {
-            issue_head(cur, 0);
-            for (int c = 0; c < WS_STAGES; ++c) issue_chunk(cur, c, c);
+            issue_obj(cur, 0);
+            for (int c = 0; c < FT_STAGES; ++c) issue_chunk(cur, c, c);
         }
         int s = 0;                       // ring stage of the next chunk to consume
         unsigned ph = 0u;                // phase bit per ring stage
-        unsigned it = 0u;                // tiles processed (head slot = it & 1, its phase = (it >> 1) & 1)
-        unsigned n_sent = 0u;            // packets handed over
-        bool have_pk = false;            // packet n_sent % WS_PK is already ours (acquired, n == 0)
+        unsigned it = 0u;                // tiles processed (objectness slot = it & 1, its phase = (it >> 1) & 1)
         while (cur.np != 0) {
             const int ahead = (nxt.np != 0) ? draw() : 0;
-            if (lane == 0 && nxt.np != 0) issue_head(nxt, (it + 1) & 1);
-            const int kslot = (int)(n_sent % WS_PK);
-            WsPacket<NW> &K = S.pk[warp][kslot];
-            if (!have_pk) {
-                mbar_wait(&S.pk_empty[warp][kslot], ((n_sent / WS_PK) & 1u) ^ 1u);      // first use: passes on the fresh barrier
-                have_pk = true;
-            }
+            if (lane == 0 && nxt.np != 0) issue_obj(nxt, (it + 1) & 1);
             const bool inb = lane * 4 < cur.np;
             float obj[4], lth[4];
-            float4 braw[4];
             {
-                mbar_wait(&W.head_full[it & 1], (it >> 1) & 1u);
-                const float *hp = &W.head[it & 1][0][lane * 4];
-                const float4 tx = *reinterpret_cast<const float4 *>(hp), ty = *reinterpret_cast<const float4 *>(hp + WT_BOX);
-                const float4 tw = *reinterpret_cast<const float4 *>(hp + 2 * WT_BOX), th = *reinterpret_cast<const float4 *>(hp + 3 * WT_BOX);
-                const float4 to = *reinterpret_cast<const float4 *>(hp + 4 * WT_BOX);
-                braw[0] = make_float4(tx.x, ty.x, tw.x, th.x); braw[1] = make_float4(tx.y, ty.y, tw.y, th.y);
-                braw[2] = make_float4(tx.z, ty.z, tw.z, th.z); braw[3] = make_float4(tx.w, ty.w, tw.w, th.w);
+                mbar_wait(&W.obj_full[it & 1], (it >> 1) & 1u);
+                const float4 to = *reinterpret_cast<const float4 *>(&W.objp[it & 1][lane * 4]);
                 const float tv[4] = {to.x, to.y, to.z, to.w};
 #pragma unroll
                 for (int v = 0; v < 4; ++v) {
@@ -1021,12 +885,13 @@ k_filter_raw_ws(const __grid_constant__ RawParams P, const __grid_constant__ Tma
                     lth[v] = inb ? class_logit_bound(obj[v], P.thr) : kInf;
                 }
             }
-            __syncwarp();                                              // the head slot has been read
-            // One flat loop over the class chunks (not unrolled over the flag words: the kernel must stay inside the instruction
-            // cache, its two roles run different code on the same SM); a finished flag word goes straight into the packet.
+            const RawLayer &Ly = P.layer[cur.layer];
+            const int b = cur.ba / 3, a = cur.ba - 3 * b;
+            const size_t r = (size_t)b * P.M4 + (Ly.row_off + a * Ly.F2 + cur.p0 + lane * 4);
+            if (inb) stg_keep4(P.objtab + r, make_uint4(__float_as_uint(obj[0]), __float_as_uint(obj[1]), __float_as_uint(obj[2]),
+                                                        __float_as_uint(obj[3])));
             constexpr int CPW = 32 / WT_KC;                              // chunks per flag word
             unsigned m0 = 0u, m1 = 0u, m2 = 0u, m3 = 0u;
-            unsigned n_queued = 0u;                                      // entries queued for this tile (warp-uniform)
 #pragma unroll 1
             for (int c = 0; c < n_cc; ++c) {
                 mbar_wait(&W.full[s], (ph >> s) & 1u);
@@ -1055,100 +920,52 @@ k_filter_raw_ws(const __grid_constant__ RawParams P, const __grid_constant__ Tma
                         flag_or(a3, tv.w, lth[3], 1u << k);
                     }
                 }
-                // a dead box (objectness below the threshold, or outside the tile) flags nothing, whatever its logits are
-                if (lth[0] == kInf) a0 = 0u;
-                if (lth[1] == kInf) a1 = 0u;
-                if (lth[2] == kInf) a2 = 0u;
-                if (lth[3] == kInf) a3 = 0u;
-                // rare (~0.6 % of the logits): queue (box slot, class, logit) while the logit is still in the stage.  Warp-
-                // cooperative: one prefix sum gives every lane its run of queue slots; the running count lives in a register
-                // (no shared-memory atomics, no per-lane loops over four words).
-                {
-                    static_assert(WT_KC == 8, "the four 8-bit chunk masks of a lane are packed into one word");
-                    unsigned am = a0 | (a1 << 8) | (a2 << 16) | (a3 << 24);
-                    if (__ballot_sync(FULL, am != 0u)) {                 // warp-uniform
-                        const int cnt = __popc(am);
-                        int incl = cnt;
-#pragma unroll
-                        for (int o = 1; o < 32; o <<= 1) {
-                            const int t = __shfl_up_sync(FULL, incl, o);
-                            if (lane >= o) incl += t;
-                        }
-                        unsigned q = n_queued + (unsigned)(incl - cnt);
-                        n_queued += (unsigned)__shfl_sync(FULL, incl, 31);
-                        while (am) {
-                            const int bit = __ffs(am) - 1;
-                            am &= am - 1u;
-                            if (q < (unsigned)WS_QCAP) {
-                                K.ent[q] = (unsigned short)(((lane * 4 + (bit >> 3)) << 8) | (c * WT_KC + (bit & 7)));
-                                K.val[q] = sp[(bit & 7) * WT_BOX + (bit >> 3)];
-                            }
-                            ++q;
-                        }
-                    }
-                }
                 const int sh = (c % CPW) * WT_KC;
                 m0 |= a0 << sh; m1 |= a1 << sh; m2 |= a2 << sh; m3 |= a3 << sh;
                 __syncwarp();                                            // every lane has read the stage
                 if (lane == 0) {
-                    const int cn = c + WS_STAGES;                        // the chunk that takes this stage next
+                    const int cn = c + FT_STAGES;                        // the chunk that takes this stage next
                     if (cn < n_cc) issue_chunk(cur, cn, s);
                     else if (nxt.np != 0) issue_chunk(nxt, cn - n_cc, s);
                 }
                 ph ^= 1u << s;
-                s = (s + 1 == WS_STAGES) ? 0 : s + 1;
+                s = (s + 1 == FT_STAGES) ? 0 : s + 1;
                 if ((c + 1) % CPW == 0 || c + 1 == n_cc) {
-                    *reinterpret_cast<uint4 *>(&K.bits[c / CPW][lane * 4]) = make_uint4(m0, m1, m2, m3);
+                    // a dead box (objectness below the threshold) flags nothing, whatever its logits are (NaN / +inf set bits)
+                    if (lth[0] == kInf) m0 = 0u;
+                    if (lth[1] == kInf) m1 = 0u;
+                    if (lth[2] == kInf) m2 = 0u;
+                    if (lth[3] == kInf) m3 = 0u;
+                    if (inb) stg_keep4(P.flags + (size_t)(c / CPW) * P.BM4 + r, make_uint4(m0, m1, m2, m3));
                     m0 = m1 = m2 = m3 = 0u;
                 }
-            }
-            __syncwarp();
-            // hand the tile over (the loop's last __syncwarp made every lane's queue entries and K.n visible)
-            if (n_queued != 0u) {                                        // warp-uniform
-                *reinterpret_cast<float4 *>(&K.sobj[lane * 4]) = make_float4(obj[0], obj[1], obj[2], obj[3]);
-#pragma unroll
-                for (int v = 0; v < 4; ++v) K.box[lane * 4 + v] = braw[v];
-                if (lane < 4) { K.any[lane] = 0u; K.nan[lane] = 0u; }
-                if (lane == 0) { K.n = n_queued; K.layer = cur.layer; K.ba = cur.ba; K.p0 = cur.p0; K.stop = 0; }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&S.pk_full[warp][kslot]);
-                ++n_sent;
-                have_pk = false;
             }
             cur = nxt;
             if (nxt.np != 0) nxt = resolve(ahead);
             ++it;
         }
-        {                                                               // tell the emit warp to stop
-            const int kslot = (int)(n_sent % WS_PK);
-            if (!have_pk) mbar_wait(&S.pk_empty[warp][kslot], ((n_sent / WS_PK) & 1u) ^ 1u);
-            if (lane == 0) S.pk[warp][kslot].stop = 1;
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&S.pk_full[warp][kslot]);
-        }
     } else {
-        // ---------------- emit warp ----------------
-        const int e = warp - WS_STREAM;
-        for (unsigned n = 0u;; ++n) {
-            const int kslot = (int)(n % WS_PK);
-            WsPacket<NW> &K = S.pk[e][kslot];
-            mbar_wait_idle(&S.pk_full[e][kslot], (n / WS_PK) & 1u);
-            if (K.stop) break;                                           // warp-uniform
-#ifndef YL_WS_NOEMIT                                                     // (diagnostic build: the streaming side alone)
-            const int cnt = (int)min(*reinterpret_cast<volatile unsigned *>(&K.n), 0x7FFFFFFFu);
-            if (cnt <= WS_QCAP) {
-                emit_packet<NW>(P, P.layer[K.layer], K, cnt);
-            } else {
-                // dense tile: more flagged pairs than the packet queues; the flag words drive the re-reading form
-                ws_fallback<NW>(P, K, S.em[e]);
+        // ---------------- scalar warp: 32 boxes per tile, register-staged loads ----------------
+        for (;;) {
+            int t = 0;
+            if (lane == 0) t = (int)atomicAdd(scalar_counter, 1u);
+            const WtTile T = ft_tile(P, __shfl_sync(FULL, t, 0), nba, 0);
+            if (T.np == 0) break;
+            const RawLayer &Ly = P.layer[T.layer];
+            float obj1[1], lth1[1];
+            unsigned bits1[1][NW];
+            const bool inb = lane < T.np;
+            ldg_stream<1, NW>(P, Ly, T.ba, T.p0 + lane, inb, obj1, lth1, bits1);
+            if (inb) {
+                const int b = T.ba / 3, a = T.ba - 3 * b;
+                const size_t r = (size_t)b * P.M4 + (Ly.row_off + a * Ly.F2 + T.p0 + lane);
+                stg_keep1(P.objtab + r, __float_as_uint(obj1[0]));
+#pragma unroll
+                for (int w = 0; w < NW; ++w) stg_keep1(P.flags + (size_t)w * P.BM4 + r, bits1[0][w]);
             }
-#endif
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&S.pk_empty[e][kslot]);
         }
     }
 }
-
 
 // grid = (sum of tiles over the scales, img_count*3): one launch covers all scales of an image group.
 template <int NW>
@@ -1357,11 +1174,13 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32
 
 // YL_NO_TMA=1 forces the register-staged LDG kernel for every scale (A/B measurements).
 static const bool g_use_tma = !(getenv("YL_NO_TMA") && getenv("YL_NO_TMA")[0] == '1');
-// YL_FILTER selects the front-end form: "split" (default: lean streaming flag kernel + emit kernel),
-// "fused" (one kernel streams and emits: the TMA pipeline where planes are 16-byte aligned, register-staged otherwise).
-// "ws" (warp-specialised persistent kernel: TMA streaming warps + emit warps, no flag table, no emit launch).
-static const bool g_ws = getenv("YL_FILTER") && strcmp(getenv("YL_FILTER"), "ws") == 0;
-static const bool g_split = !g_ws && !(getenv("YL_FILTER") && strcmp(getenv("YL_FILTER"), "fused") == 0);
+// YL_FILTER selects the front-end form: "split" (default: streaming flag kernel + emit kernel) or "fused" (one kernel streams
+// and emits: the TMA pipeline where planes are 16-byte aligned, register-staged otherwise; measured slower, kept for A/B).
+static const bool g_split = !(getenv("YL_FILTER") && strcmp(getenv("YL_FILTER"), "fused") == 0);
+// YL_FLAG selects the streaming kernel of the split form: "ldg" (k_flag_raw: register-staged loads, fills the register file) or
+// "tma" (k_flag_tma: one persistent CTA per SM, TMA rings in shared memory, a quarter of the register file -- the form that
+// lets the emit / NMS CTAs of the previous image group run next to it).
+static const bool g_flag_tma = getenv("YL_FLAG") ? strcmp(getenv("YL_FLAG"), "tma") == 0 : false;
 // YL_FLAG_SMEM=<bytes, at most 48 KB>: dynamic shared memory requested (and not used) by k_flag_raw, which caps its CTAs per
 // SM so that CTAs of other kernels can be co-resident (cross-step pipelining experiments, tools/xstep_probe.py).
 static const int g_flag_smem = getenv("YL_FLAG_SMEM") ? atoi(getenv("YL_FLAG_SMEM")) : 0;
@@ -1382,29 +1201,6 @@ static int encode_plane_map(CUtensorMap *map, const float *raw, int F2, long row
     const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)raw, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? YL_OK : YL_ERR_CUDA_BASE + (int)cudaErrorInvalidValue;
-}
-
-// Side streams of the warp-specialised form: the unaligned scales' flag / emit kernels are forked off the caller's stream
-// and joined again behind the persistent kernel (event record / wait; capturable into a CUDA graph).  One side stream and
-// event pair per (device, caller stream), created on first use and kept for the life of the process.
-struct SideLane { int dev; cudaStream_t user, side; cudaEvent_t fork, join; };
-static std::mutex g_side_mu;
-static std::vector<SideLane> g_side;
-static int side_lane(cudaStream_t user, SideLane *out)
-{
-    int dev = 0;
-    YL_CUDA_TRY(cudaGetDevice(&dev));
-    std::lock_guard<std::mutex> lk(g_side_mu);
-    for (const SideLane &l : g_side)
-        if (l.dev == dev && l.user == user) { *out = l; return YL_OK; }
-    SideLane l;
-    l.dev = dev; l.user = user;
-    YL_CUDA_TRY(cudaStreamCreateWithFlags(&l.side, cudaStreamNonBlocking));
-    YL_CUDA_TRY(cudaEventCreateWithFlags(&l.fork, cudaEventDisableTiming));
-    YL_CUDA_TRY(cudaEventCreateWithFlags(&l.join, cudaEventDisableTiming));
-    g_side.push_back(l);
-    *out = l;
-    return YL_OK;
 }
 
 static int g_num_sms()
@@ -1444,24 +1240,25 @@ static int filter_raw_impl(const float *const *raw, const int *F, int n_layers, 
     const PostLayout L = post_layout(B, M, C, cap_seg);
     if (ws_bytes < L.total) return YL_ERR_WORKSPACE;
     if (img_count == 0) return YL_OK;
+    const int NW = (C + 31) / 32;
+    if (NW < 1 || NW > 4) return YL_ERR_CLASSES;
     char *w = (char *)ws;
-    unsigned *seg_count = (unsigned *)(w + L.off_seg_count);
-    uint4 *cand = (uint4 *)(w + L.off_cand);
-    float *objtab = (float *)(w + L.off_obj);
+    cudaStream_t st = (cudaStream_t)stream;
     RawParams base;
     base.C = C; base.cap_seg = cap_seg; base.img_first = img_first; base.M = M; base.thr = conf_thre;
     base.sparse = conf_thre >= 0.02f ? 1 : 0;     // sigmoid(obj) >= 0.02 is rare for background cells (obj logit >= -3.9)
-    base.cand = cand; base.seg_count = seg_count; base.objtab = objtab; base.n_layers = 0;
+    base.cand = (uint4 *)(w + L.off_cand); base.seg_count = (unsigned *)(w + L.off_seg_count);
+    base.objtab = (float *)(w + L.off_obj); base.n_layers = 0;
     base.flags = (unsigned *)(w + L.off_flags); base.M4 = L.M4; base.BM4 = (long)B * L.M4;
     base.reset = (unsigned *)w; base.reset_words = 0;
-    if (stages & 4) {
-        // the caller skips yl_post_reset: the split form's flag kernel zeroes the counters, every other form gets a memset
-        if (g_split && (stages & 1)) base.reset_words = (int)(L.counters_bytes / sizeof(unsigned));
-        else YL_CUDA_TRY(cudaMemsetAsync(ws, 0, L.counters_bytes, (cudaStream_t)stream));
-    }
-    RawParams Pt = base, Pl = base;                 // Pt: persistent TMA kernel (TMA scales first, scalar scales last); Pl: LDG kernel
+
+    // ---- the scales as the kernels see them ----
     RawLayer lay[3];
-    int row_off = 0, tiles_tma = 0, tiles_ldg = 0, n_tma = 0;
+    int row_off = 0, n_tma = 0;
+    const int n_cc = (C + WT_KC - 1) / WT_KC;
+    // the TMA flag kernel streams every plane of every box; with a high threshold the register-staged kernel's objectness-first
+    // mode skips most class planes instead
+    const bool flag_tma = g_split && g_flag_tma && !base.sparse;
     for (int l = 0; l < n_layers; ++l) {
         RawLayer &Ly = lay[l];
         Ly.raw = raw[l]; Ly.Fw = F[l]; Ly.F2 = F[l] * F[l]; Ly.row_off = row_off;
@@ -1474,21 +1271,26 @@ static int filter_raw_impl(const float *const *raw, const int *F, int n_layers, 
         }
         // 128-bit loads / bulk copies need 16-byte aligned planes: F^2 % 4 == 0 and an aligned base (19x19, 13x13 fall back)
         Ly.vec = ((Ly.F2 % 4 == 0) && (((uintptr_t)raw[l]) % 16 == 0)) ? 4 : 1;
-        Ly.tma = (Ly.vec == 4 && g_use_tma && (C + WT_KC - 1) / WT_KC >= (g_ws ? WS_STAGES : WT_STAGES)) ? 1 : 0;
+        Ly.tma = (Ly.vec == 4 && g_use_tma && n_cc >= (flag_tma ? FT_STAGES : WT_STAGES)) ? 1 : 0;
+        Ly.tile_boxes = 0; Ly.tiles = 0;
         n_tma += Ly.tma;
         row_off += 3 * Ly.F2;
     }
-    if (g_split) n_tma = 0;
+    // Pt: persistent TMA kernels (warp tiles of 128 boxes, 32 for the scalar scales; TMA scales first).  Pl: the grid kernels
+    // (k_flag_raw / k_emit_flagged / k_filter_raw: CTA tiles of K1_THREADS * vec boxes).
+    const bool persistent = n_tma > 0 && (flag_tma || !g_split);
+    RawParams Pt = base, Pl = base;
+    int tiles_tma = 0, tiles_ldg = 0;
     for (int pass = 0; pass < 2; ++pass)
         for (int l = 0; l < n_layers; ++l) {
             RawLayer Ly = lay[l];
-            if (n_tma > 0 && !(g_ws && !Ly.tma)) {                            // goes through the persistent kernel
-                if ((pass == 0) != (Ly.tma == 1)) continue;
+            if (persistent && (pass == 0) == (Ly.tma == 1)) {
                 Ly.tile_boxes = Ly.tma ? WT_BOX : 32;
                 Ly.tiles = (Ly.F2 + Ly.tile_boxes - 1) / Ly.tile_boxes;
                 tiles_tma += Ly.tiles;
                 Pt.layer[Pt.n_layers++] = Ly;
-            } else if (pass == 0) {
+            }
+            if (pass == 0 && (g_split || !persistent)) {
                 Ly.tma = 0;
                 Ly.tile_boxes = K1_THREADS * Ly.vec;
                 Ly.tiles = (Ly.F2 / Ly.vec + K1_THREADS - 1) / K1_THREADS;
@@ -1496,77 +1298,57 @@ static int filter_raw_impl(const float *const *raw, const int *F, int n_layers, 
                 Pl.layer[Pl.n_layers++] = Ly;
             }
         }
-    for (int l = Pt.n_layers; l < 3; ++l) { Pt.layer[l] = Pt.layer[0]; Pt.layer[l].tiles = 0; }
-    for (int l = Pl.n_layers; l < 3; ++l) { Pl.layer[l] = Pl.layer[0]; Pl.layer[l].tiles = 0; }
-    cudaStream_t st = (cudaStream_t)stream;
-    const int NW = (C + 31) / 32;
-    if (NW < 1 || NW > 4) return YL_ERR_CLASSES;
-    // warp-specialised form: the scales the persistent kernel does not take (unaligned planes) are forked onto a side stream
-    // and run next to it through the split kernels; joined below
-    cudaStream_t st_l = st;
-    SideLane lane;
-    bool forked = false;
-    if (g_ws && Pt.n_layers > 0 && Pl.n_layers > 0) {
-        const int rc = side_lane(st, &lane);
-        if (rc != YL_OK) return rc;
-        YL_CUDA_TRY(cudaEventRecord(lane.fork, st));
-        YL_CUDA_TRY(cudaStreamWaitEvent(lane.side, lane.fork, 0));
-        st_l = lane.side;
-        forked = true;
-    }
-    auto launch_ldg = [&]() -> int {
-        if (Pl.n_layers > 0) {
-            dim3 grid(tiles_ldg, img_count * 3);
-            if (g_split || g_ws) {
-                if (stages & 1) {
-                    switch (NW) {
-                    case 1: k_flag_raw<1><<<grid, K1_THREADS, g_flag_smem, st_l>>>(Pl); break;
-                    case 2: k_flag_raw<2><<<grid, K1_THREADS, g_flag_smem, st_l>>>(Pl); break;
-                    case 3: k_flag_raw<3><<<grid, K1_THREADS, g_flag_smem, st_l>>>(Pl); break;
-                    default: k_flag_raw<4><<<grid, K1_THREADS, g_flag_smem, st_l>>>(Pl); break;
-                    }
-                    YL_LAUNCH_CHECK();
-                }
-                if (stages & 2) {
-                    const bool pdl = pdl_enabled() && (stages & 1);             // directly behind k_flag_raw on the stream
-                    cudaError_t le;
-                    switch (NW) {
-                    case 1: le = launch_after(k_emit_flagged<1>, grid, dim3(K1_THREADS), 0, st_l, pdl, Pl); break;
-                    case 2: le = launch_after(k_emit_flagged<2>, grid, dim3(K1_THREADS), 0, st_l, pdl, Pl); break;
-                    case 3: le = launch_after(k_emit_flagged<3>, grid, dim3(K1_THREADS), 0, st_l, pdl, Pl); break;
-                    default: le = launch_after(k_emit_flagged<4>, grid, dim3(K1_THREADS), 0, st_l, pdl, Pl); break;
-                    }
-                    if (le != cudaSuccess) return YL_ERR_CUDA_BASE + (int)le;
-                }
-            } else {
-                switch (NW) {
-                case 1: k_filter_raw<1><<<grid, K1_THREADS, 0, st_l>>>(Pl); break;
-                case 2: k_filter_raw<2><<<grid, K1_THREADS, 0, st_l>>>(Pl); break;
-                case 3: k_filter_raw<3><<<grid, K1_THREADS, 0, st_l>>>(Pl); break;
-                default: k_filter_raw<4><<<grid, K1_THREADS, 0, st_l>>>(Pl); break;
-                }
-            }
-            YL_LAUNCH_CHECK();
+    for (int l = Pt.n_layers; l < 3; ++l) { Pt.layer[l] = lay[0]; Pt.layer[l].tiles = 0; Pt.layer[l].tma = -1; }
+    for (int l = Pl.n_layers; l < 3; ++l) { Pl.layer[l] = lay[0]; Pl.layer[l].tiles = 0; }
+
+    // ---- counters (stages bit 2: the caller skipped yl_post_reset) ----
+    if (stages & 4) {
+        if (g_split && (stages & 1) && flag_tma && persistent) {
+            // the TMA flag kernel zeroes the segment counters itself, but not the two tile counters it draws from
+            Pt.reset_words = (int)(L.off_tile_count / sizeof(unsigned));
+            YL_CUDA_TRY(cudaMemsetAsync(w + L.off_tile_count, 0, L.counters_bytes - L.off_tile_count, st));
+        } else if (g_split && (stages & 1)) {
+            Pl.reset_words = (int)(L.counters_bytes / sizeof(unsigned));   // k_flag_raw zeroes the counters (no memset node)
+        } else {
+            YL_CUDA_TRY(cudaMemsetAsync(ws, 0, L.counters_bytes, st));
         }
-        return YL_OK;
-    };
-    // forked: the persistent kernel is enqueued first so that its one CTA per SM is placed before the side stream's CTAs
-    if (!forked) { const int rc = launch_ldg(); if (rc != YL_OK) return rc; }
-    if (Pt.n_layers > 0 && (!g_ws || (stages & 1))) {
+    }
+
+    // ---- persistent TMA kernels ----
+    if (persistent && (stages & 1)) {
         const int nba = img_count * 3;
-        const int n_tiles = nba * tiles_tma;                                 // warp tiles
-        const size_t smem = sizeof(WtSmem);
-        const int ctas_per_sm = (int)((227 * 1024) / (smem + 1024));
-        const int want = (n_tiles + K1_WARPS - 1) / K1_WARPS;
-        const int grid = want < ctas_per_sm * g_num_sms() ? want : ctas_per_sm * g_num_sms();
         unsigned *tile_counter = (unsigned *)(w + L.off_tile_count) + img_first;
+        unsigned *scalar_counter = (unsigned *)(w + L.off_tile_count) + B + img_first;
         TmaMaps maps;
         memset(&maps, 0, sizeof(maps));
+        int n_tma_tiles = 0;
         for (int l = 0; l < Pt.n_layers; ++l) {
-            if (!Pt.layer[l].tma) continue;
+            if (Pt.layer[l].tma != 1) continue;
+            n_tma_tiles += Pt.layer[l].tiles * nba;
             const int rc = encode_plane_map(&maps.m[l], Pt.layer[l].raw, Pt.layer[l].F2, (long)B * 3 * (5 + C));
             if (rc != YL_OK) return rc;
         }
+        if (flag_tma) {
+            const size_t smem = sizeof(FtSmem);
+            const int want = (n_tma_tiles + FT_STREAM - 1) / FT_STREAM;
+            const int grid = want < g_num_sms() ? (want > 0 ? want : 1) : g_num_sms();
+#define YL_FT_CASE(NW_)                                                                                              \
+    case NW_: {                                                                                                      \
+        static bool attr_done = false;                                                                               \
+        if (!attr_done) {                                                                                            \
+            YL_CUDA_TRY(cudaFuncSetAttribute(k_flag_tma<NW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            attr_done = true;                                                                                        \
+        }                                                                                                            \
+        k_flag_tma<NW_><<<grid, FT_THREADS, smem, st>>>(Pt, maps, nba, tile_counter, scalar_counter);                 \
+    } break;
+            switch (NW) { YL_FT_CASE(1) YL_FT_CASE(2) YL_FT_CASE(3) YL_FT_CASE(4) }
+#undef YL_FT_CASE
+        } else {
+            const int n_tiles = nba * tiles_tma;                             // warp tiles, TMA and scalar
+            const size_t smem = sizeof(WtSmem);
+            const int ctas_per_sm = (int)((227 * 1024) / (smem + 1024));
+            const int want = (n_tiles + K1_WARPS - 1) / K1_WARPS;
+            const int grid = want < ctas_per_sm * g_num_sms() ? want : ctas_per_sm * g_num_sms();
 #define YL_TMA_CASE(NW_)                                                                                             \
     case NW_: {                                                                                                      \
         static bool attr_done = false;                                                                               \
@@ -1574,40 +1356,47 @@ static int filter_raw_impl(const float *const *raw, const int *F, int n_layers, 
             YL_CUDA_TRY(cudaFuncSetAttribute(k_filter_raw_tma<NW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
             attr_done = true;                                                                                        \
         }                                                                                                            \
-        k_filter_raw_tma<NW_><<<grid, K1_THREADS, smem, st>>>(Pt, maps, nba, n_tiles, tile_counter);                       \
+        k_filter_raw_tma<NW_><<<grid, K1_THREADS, smem, st>>>(Pt, maps, nba, n_tiles, tile_counter);                  \
     } break;
-#define YL_WS_CASE(NW_)                                                                                              \
-    case NW_: {                                                                                                      \
-        static bool attr_done = false;                                                                               \
-        const size_t smem_ws = sizeof(WsSmem<NW_>);                                                                  \
-        if (!attr_done) {                                                                                            \
-            YL_CUDA_TRY(cudaFuncSetAttribute(k_filter_raw_ws<NW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ws)); \
-            attr_done = true;                                                                                        \
-        }                                                                                                            \
-        const int want_ws = (n_tiles + WS_STREAM - 1) / WS_STREAM;                                                   \
-        const int grid_ws = want_ws < g_num_sms() ? want_ws : g_num_sms();                                           \
-        k_filter_raw_ws<NW_><<<grid_ws, WS_THREADS, smem_ws, st>>>(Pt, wmaps, nba, tile_counter);                     \
-    } break;
-        if (g_ws) {
-            TmaMapsWs wmaps;
-            memset(&wmaps, 0, sizeof(wmaps));
-            for (int l = 0; l < Pt.n_layers; ++l) {
-                wmaps.cls[l] = maps.m[l];
-                const int rc = encode_plane_map(&wmaps.head[l], Pt.layer[l].raw, Pt.layer[l].F2, (long)B * 3 * (5 + C), WS_HEAD);
-                if (rc != YL_OK) return rc;
-            }
-            switch (NW) { YL_WS_CASE(1) YL_WS_CASE(2) YL_WS_CASE(3) YL_WS_CASE(4) }
-        }
-        else switch (NW) { YL_TMA_CASE(1) YL_TMA_CASE(2) YL_TMA_CASE(3) YL_TMA_CASE(4) }
-#undef YL_WS_CASE
+            switch (NW) { YL_TMA_CASE(1) YL_TMA_CASE(2) YL_TMA_CASE(3) YL_TMA_CASE(4) }
 #undef YL_TMA_CASE
+        }
         YL_LAUNCH_CHECK();
     }
-    if (forked) {
-        const int rc = launch_ldg();
-        if (rc != YL_OK) return rc;
-        YL_CUDA_TRY(cudaEventRecord(lane.join, lane.side));
-        YL_CUDA_TRY(cudaStreamWaitEvent(st, lane.join, 0));
+
+    // ---- grid kernels ----
+    if (Pl.n_layers > 0) {
+        dim3 grid(tiles_ldg, img_count * 3);
+        if (g_split) {
+            if ((stages & 1) && !(flag_tma && persistent)) {
+                switch (NW) {
+                case 1: k_flag_raw<1><<<grid, K1_THREADS, g_flag_smem, st>>>(Pl); break;
+                case 2: k_flag_raw<2><<<grid, K1_THREADS, g_flag_smem, st>>>(Pl); break;
+                case 3: k_flag_raw<3><<<grid, K1_THREADS, g_flag_smem, st>>>(Pl); break;
+                default: k_flag_raw<4><<<grid, K1_THREADS, g_flag_smem, st>>>(Pl); break;
+                }
+                YL_LAUNCH_CHECK();
+            }
+            if (stages & 2) {
+                const bool pdl = pdl_enabled() && (stages & 1);             // directly behind the flag kernel on the stream
+                cudaError_t le;
+                switch (NW) {
+                case 1: le = launch_after(k_emit_flagged<1>, grid, dim3(K1_THREADS), 0, st, pdl, Pl); break;
+                case 2: le = launch_after(k_emit_flagged<2>, grid, dim3(K1_THREADS), 0, st, pdl, Pl); break;
+                case 3: le = launch_after(k_emit_flagged<3>, grid, dim3(K1_THREADS), 0, st, pdl, Pl); break;
+                default: le = launch_after(k_emit_flagged<4>, grid, dim3(K1_THREADS), 0, st, pdl, Pl); break;
+                }
+                if (le != cudaSuccess) return YL_ERR_CUDA_BASE + (int)le;
+            }
+        } else if (stages & 1) {
+            switch (NW) {
+            case 1: k_filter_raw<1><<<grid, K1_THREADS, 0, st>>>(Pl); break;
+            case 2: k_filter_raw<2><<<grid, K1_THREADS, 0, st>>>(Pl); break;
+            case 3: k_filter_raw<3><<<grid, K1_THREADS, 0, st>>>(Pl); break;
+            default: k_filter_raw<4><<<grid, K1_THREADS, 0, st>>>(Pl); break;
+            }
+            YL_LAUNCH_CHECK();
+        }
     }
     return YL_OK;
 }

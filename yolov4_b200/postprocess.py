@@ -212,6 +212,7 @@ class HeadPostprocessor:
             self.rows = torch.empty((self.B, self.cap_out, 7), dtype=torch.float32, device=self.device)
             self.meta = torch.zeros((3 * self.B,), dtype=torch.int32, device=self.device)
             self.side = torch.cuda.Stream(device=self.device, priority=side_priority)
+            self.side2 = torch.cuda.Stream(device=self.device, priority=side_priority)
         self.mode = mode
         self.graph = None
         # kernels launched per run(): per group flag + emit + segment NMS + fix-up (+ 1 memset node)
@@ -226,7 +227,7 @@ class HeadPostprocessor:
         rp = _cabi.ptrs([r.data_ptr() for r in raws])
         main = torch.cuda.current_stream(self.device)
         G = self.n_groups
-        fold_reset = (G == 1 and self.mode != "emit_side")    # one group: the flag kernel zeroes the counters itself
+        fold_reset = (G == 1 and self.mode not in ("emit_side", "pipe3"))    # one group: the flag kernel zeroes the counters itself
         if not fold_reset:
             _cabi.check(L.yl_post_reset(self.ws.ptr(), self.ws.nbytes, B, M, C, self.cap_seg, main.cuda_stream))
         for g in range(G):
@@ -235,7 +236,7 @@ class HeadPostprocessor:
                 _cabi.check(L.yl_filter_raw_stage(rp, self.fs, len(self.Fs), B, C, self.anch, self.mask, self.conf, self.ws.ptr(),
                                                   self.ws.nbytes, M, self.cap_seg, i0, i1 - i0, 7, main.cuda_stream))
                 self.side.wait_stream(main)
-            elif self.mode == "emit_side":
+            elif self.mode in ("emit_side", "pipe3"):
                 # streaming flag kernels back to back on the main stream; everything else follows on the side stream
                 _cabi.check(L.yl_filter_raw_stage(rp, self.fs, len(self.Fs), B, C, self.anch, self.mask, self.conf, self.ws.ptr(),
                                                   self.ws.nbytes, M, self.cap_seg, i0, i1 - i0, 1, main.cuda_stream))
@@ -246,9 +247,16 @@ class HeadPostprocessor:
                 _cabi.check(L.yl_filter_raw(rp, self.fs, len(self.Fs), B, C, self.anch, self.mask, self.conf, self.ws.ptr(),
                                             self.ws.nbytes, M, self.cap_seg, i0, i1 - i0, main.cuda_stream))
                 self.side.wait_stream(main)
+            nms_stream = self.side
+            if self.mode == "pipe3":
+                # three-deep: flag(g+1) on the main stream, emit(g) on the first side stream, NMS + gather(g-1) on the second
+                self.side2.wait_stream(self.side)
+                nms_stream = self.side2
             _cabi.check(L.yl_nms(self.ws.ptr(), self.ws.nbytes, B, M, C, self.cap_seg, self.nms, self.rows.data_ptr(),
-                                 self.cap_out, self.meta.data_ptr(), i0, i1 - i0, self.side.cuda_stream))
+                                 self.cap_out, self.meta.data_ptr(), i0, i1 - i0, nms_stream.cuda_stream))
         main.wait_stream(self.side)
+        if self.mode == "pipe3":
+            main.wait_stream(self.side2)
         return self.rows, self.meta
 
     def capture(self, head_outputs):
