@@ -264,10 +264,18 @@ def extras(torch, yb, dev, peak):
     def bt():
         for l in range(3):
             crit.build_target(outs[l]["output"], outs[l]["pred"], l, labels)
+
+    def bt3():
+        yb.build_targets3([o["output"] for o in outs], [o["pred"] for o in outs], [0, 1, 2], labels, yb.ANCHORS_PX, yb.ANCHOR_MASK,
+                          0.7, C)
     t = time_events(torch, bt, 10)
-    out["config4_build_target_b64_50gt"] = {"us_per_step": t * 1e6, "images_per_s": B / t,
-                                            "write_roofline_frac": B * TARGET_BYTES_PER_IMAGE / t / 1e9 / peak,
-                                            "bytes_per_image": TARGET_BYTES_PER_IMAGE}
+    t3 = time_events(torch, bt3, 10)
+    out["config4_build_target_b64_50gt"] = {"us_per_step": t3 * 1e6, "images_per_s": B / t3,
+                                            "write_roofline_frac": B * TARGET_BYTES_PER_IMAGE / t3 / 1e9 / peak,
+                                            "bytes_per_image": TARGET_BYTES_PER_IMAGE,
+                                            "form": "yl_build_target3: one launch pair for the three scales (YOLOLoss.forward)",
+                                            "three_per_layer_calls_us": t * 1e6,
+                                            "note": "includes the allocation of the four dense output tensors per scale (torch.empty)"}
 
     def dec_train():
         with torch.no_grad():
@@ -522,12 +530,34 @@ def main():
             t = torch.tensor([dt], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
+        # the platform's ceiling for this leg, measured here: the same pinned buffers uploaded by plain copies, no kernel, all
+        # ranks at once (at N>1 the ranks share the host's memory system and PCIe root complexes)
+        dev_in = [torch.empty_like(r) for r in raws]
+        for h, d in zip(host, dev_in):
+            d.copy_(h, non_blocking=True)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(max(3, args.e2e_steps)):
+            for h, d in zip(host, dev_in):
+                d.copy_(h, non_blocking=True)
+        torch.cuda.synchronize()
+        dt_probe = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt_probe], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt_probe = float(t.item())
+        h2d_probe_gbs = sum(h.numel() * 4 for h in host) * max(3, args.e2e_steps) / dt_probe / 1e9
+        del dev_in
         host_rows = [out_rows[b, :int(out_cnt[b])] if int(out_cnt[b]) else None for b in range(B)]
         assert rows_equal(host_rows, res), "host path and device path disagree"
         h2d = int(sum(h.numel() * 4 for h in host))
         e2e = {"value": world * B * args.e2e_steps / dt, "unit": UNIT,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(rows_per_step * 28 + 3 * B * 4), "steps": args.e2e_steps,
                "bound": "host-to-device copies (PCIe): %.1f GB/s per rank of pinned uploads inside the timed region" % (h2d * args.e2e_steps / dt / 1e9),
+               "h2d_gbs_per_rank": h2d * args.e2e_steps / dt / 1e9,
+               "h2d_probe_gbs_per_rank": h2d_probe_gbs,
+               "h2d_probe": "the same pinned buffers uploaded by bare copies (no kernels), all %d ranks at once, max over ranks: the "
+                            "platform's ceiling for this leg; e2e reaches %.0f %% of it" % (world, 100 * (h2d * args.e2e_steps / dt / 1e9) / h2d_probe_gbs),
                "parity": "rows returned to the host == rows of the device path, bit-exact"}
         _cabi.check(L.yl_context_destroy(ctx))
 

@@ -139,6 +139,14 @@ int yl_build_target(const float *pred, const long *pred_strides, const float *la
                     int C, int layer_no, const float *anchors_px, const int *anchor_mask3, float ignore_thre,
                     float *target, float *obj_mask, float *tgt_mask, float *tgt_scale, int *status,
                     yl_stream_t stream);
+/* The same for up to three scales in ONE pair of launches (the form YOLOLoss.forward uses, yololoss.py:381-393 loops over the
+ * layers): the small grids' latency-bound CTAs run next to the 76x76 ones.  pred[l] / target[l] / ... per scale as above,
+ * ps15 = the n_layers stride quintuples back to back, F[l] the grid sizes, layer_no[l] the scale numbers, anchor_mask = the
+ * full 3x3 mask table (row layer_no[l] is used).  Results are identical to n_layers calls of yl_build_target. */
+int yl_build_target3(const float *const *pred, const long *ps15, const float *labels, int B, const int *F, int K,
+                     int C, int n_layers, const int *layer_no, const float *anchors_px, const int *anchor_mask,
+                     float ignore_thre, float *const *target, float *const *obj_mask, float *const *tgt_mask,
+                     float *const *tgt_scale, int *status, yl_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * N1  per-detection epilogue of the reference's callers

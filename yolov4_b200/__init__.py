@@ -10,7 +10,7 @@ library is missing.
 """
 from .postprocess import postprocess, detect_raw, HeadPostprocessor, ANCHORS_PX, ANCHOR_MASK  # noqa: F401
 from .yololayer import YOLOLayer, decode_dense_cat  # noqa: F401
-from .yololoss import YOLOLoss, build_target, fused_yolo_loss, fused_yolo_loss_components  # noqa: F401
+from .yololoss import YOLOLoss, build_target, build_targets3, fused_yolo_loss, fused_yolo_loss_components  # noqa: F401
 from .patch import patch_reference  # noqa: F401
 from .epilogue import coco_rows, coco_dicts, detect_rows, coco_rows_padded  # noqa: F401
 

@@ -71,6 +71,8 @@ def lib():
     L.yl_nms.argtypes = [_p, _sz, _i, _l, _i, _i, _f, _p, _l, _p, _i, _i, _p]
     L.yl_build_target.restype = _i
     L.yl_build_target.argtypes = [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _f, _p, _p, _p, _p, _p, _p]
+    L.yl_build_target3.restype = _i
+    L.yl_build_target3.argtypes = [_p, _p, _p, _i, _p, _i, _i, _i, _p, _p, _p, _f, _p, _p, _p, _p, _p, _p]
     L.yl_coco_rows.restype = _i
     L.yl_coco_rows.argtypes = [_p, _p, _l, _p, _p, _p, _i, _i, _p, _p]
     L.yl_coco_rows_padded.restype = _i
@@ -116,7 +118,7 @@ def lib():
 
 EXPORTS = [
     "yl_abi_version", "yl_source_hash", "yl_error_string", "yl_selftest_rcp", "yl_decode_dense", "yl_decode_train", "yl_decode_train_backward", "yl_decode_train_backward_raw",
-    "yl_post_workspace_bytes", "yl_post_reset", "yl_filter_raw", "yl_filter_raw_stage", "yl_filter_dense", "yl_nms", "yl_build_target", "yl_coco_rows", "yl_coco_rows_padded",
+    "yl_post_workspace_bytes", "yl_post_reset", "yl_filter_raw", "yl_filter_raw_stage", "yl_filter_dense", "yl_nms", "yl_build_target", "yl_build_target3", "yl_coco_rows", "yl_coco_rows_padded",
     "yl_loss_forward", "yl_loss_forward_chained", "yl_loss_backward",
     "yl_context_create", "yl_context_destroy", "yl_detect_host",
     "yl_xchg_create", "yl_xchg_destroy", "yl_xchg_handle_bytes", "yl_xchg_local_handle", "yl_xchg_connect", "yl_xchg_push",

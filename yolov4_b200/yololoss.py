@@ -79,6 +79,39 @@ def build_target(output, pred, layer_no, labels, anchors, anchor_mask, ignore_th
     return target, obj_mask, tgt_mask, tgt_scale
 
 
+def build_targets3(outputs, preds, layer_nos, labels, anchors, anchor_mask, ignore_thresh, n_classes):
+    """build_target for up to three scales with ONE pair of launches (yl_build_target3): the list of
+    (target, obj_mask, tgt_mask, tgt_scale) tuples that per-layer build_target calls return, bit for bit.  This is the form
+    YOLOLoss.forward uses; the per-layer method stays for callers of the reference's own API (yololoss.py:393)."""
+    if not 1 <= len(preds) <= 3 or len(outputs) != len(preds) or len(layer_nos) != len(preds):
+        raise ValueError("1..3 scales, one output / pred / layer number each")
+    dev = preds[0].device
+    n_ch = 5 + n_classes
+    lab = upload_labels(labels, dev)
+    B, K = int(lab.shape[0]), int(lab.shape[1])
+    res, Fs, strides_all = [], [], []
+    for o, p in zip(outputs, preds):
+        if not p.is_cuda or p.dtype != torch.float32 or p.device != dev:
+            raise TypeError("build_target (B200) needs float32 CUDA tensors on one device; there is no CPU fallback")
+        F = int(o.shape[2])
+        assert o.shape[-1] == n_ch and int(o.shape[1]) == 3 and int(o.shape[0]) == B
+        res.append((torch.empty((B, 3, F, F, n_ch), dtype=torch.float32, device=dev),
+                    torch.empty((B, 3, F, F), dtype=torch.float32, device=dev),
+                    torch.empty((B, 3, F, F, 4 + n_classes), dtype=torch.float32, device=dev),
+                    torch.empty((B, 3, F, F, 2), dtype=torch.float32, device=dev)))
+        Fs.append(F)
+        strides_all += list(p.stride())
+    status = torch.empty((1,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _cabi.check(_cabi.lib().yl_build_target3(
+            _cabi.ptrs([p.data_ptr() for p in preds]), _cabi.longs(strides_all), lab.data_ptr(), B, _cabi.ints(Fs), K, n_classes,
+            len(preds), _cabi.ints(layer_nos), _cabi.floats([v for wh in anchors for v in wh]),
+            _cabi.ints([v for m in anchor_mask for v in m]), float(np.float32(ignore_thresh)),
+            _cabi.ptrs([r[0].data_ptr() for r in res]), _cabi.ptrs([r[1].data_ptr() for r in res]),
+            _cabi.ptrs([r[2].data_ptr() for r in res]), _cabi.ptrs([r[3].data_ptr() for r in res]), status.data_ptr(), _stream()))
+    return res
+
+
 class YOLOLoss(nn.Module):
     strides = [8, 16, 32]
 
@@ -105,14 +138,17 @@ class YOLOLoss(nn.Module):
     def forward(self, outputs, targets):
         assert isinstance(outputs, list) and isinstance(targets, dict)
         total = 0
-        labels = None
-        for od in outputs:
-            layer_no = od['layer_no']
-            output = od['output'].to(self.device)
-            pred = od['pred'].to(self.device)
-            if labels is None:
-                labels = upload_labels(targets['padded_labels'], pred.device)      # once for the three layers (N4)
-            target, obj_mask, tgt_mask, tgt_scale = self.build_target(output, pred, layer_no, labels)
+        outs = [od['output'].to(self.device) for od in outputs]
+        preds = [od['pred'].to(self.device) for od in outputs]
+        layer_nos = [int(od['layer_no']) for od in outputs]
+        labels = upload_labels(targets['padded_labels'], preds[0].device)          # once for the three layers (N4)
+        if 1 <= len(outputs) <= 3:
+            # one pair of launches for all scales (the reference loops: yololoss.py:381-393); same tensors, bit for bit
+            built = build_targets3(outs, preds, layer_nos, labels, self.anchors, self.cfg['ANCHOR_MASK'], self.ignore_thresh,
+                                   self.n_classes)
+        else:
+            built = [self.build_target(o, p, l, labels) for o, p, l in zip(outs, preds, layer_nos)]
+        for output, (target, obj_mask, tgt_mask, tgt_scale) in zip(outs, built):
             n_ch = output.shape[-1]
             sel = np.r_[0:4, 5:n_ch]
             # yololoss.py:402-414 (written out of place; same values)
