@@ -362,30 +362,12 @@ def main():
     if world > 1:
         from yolov4_b200.sharded import DetectionExchange
         ex = DetectionExchange(B, hp.cap_out, dev, slots=2)
-        side = torch.cuda.Stream(device=dev)
-        # One CUDA graph per slot parity: the chain of step i (main branch, into rows[s]) next to the exchange of step i-1 (side
-        # branch: push rows[1-s] into every rank's window over NVLink, wait for everybody's rows of that slot, release it).
-        pipe = []
-        for s in range(2):
-            def body(s=s):
-                main = torch.cuda.current_stream(dev)
-                side.wait_stream(main)
-                with torch.cuda.stream(side):
-                    ex.push(hps[1 - s].rows, hps[1 - s].meta, 1 - s)
-                    ex.wait(1 - s)
-                    ex.release(1 - s)
-                hps[s].run(raws)
-                main.wait_stream(side)
-            st = torch.cuda.Stream(device=dev)
-            st.wait_stream(torch.cuda.current_stream(dev))
-            with torch.cuda.stream(st):
-                body()                                   # warm-up outside capture (also a consistent first exchange on all ranks)
-            torch.cuda.current_stream(dev).wait_stream(st)
-            torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                body()
-            pipe.append(g)
+        side = torch.cuda.Stream(device=dev, priority=int(os.environ.get("YL_XCHG_PRIO", "0")))
+        ev_done = [torch.cuda.Event(), torch.cuda.Event()]
+        ev_pushed = [torch.cuda.Event(), torch.cuda.Event()]
+        for e in ev_pushed:
+            e.record()
+        pipe = True
 
     def barrier():
         if world > 1:
@@ -395,20 +377,30 @@ def main():
     state = {"i": 0}
 
     def step():
+        """One step.  At N>1: the chain of step i (CUDA graph, into rows[i % 2]) on the main stream; its exchange (push the kept rows
+        into every rank's window over NVLink, wait for everybody's rows of that slot, release it) follows on the side stream and
+        runs under the chain of step i+1; the chain of step i+2 waits for it before it overwrites rows[i % 2]."""
         if pipe is None:
             hp.replay()
-        else:
-            pipe[state["i"] & 1].replay()
-            state["i"] += 1
-
-    def drain():
-        """The exchange of the last step (its rows are still local): push + wait + release on the current stream."""
-        if pipe is not None:
-            s = (state["i"] - 1) & 1
+            return
+        s = state["i"] & 1
+        main = torch.cuda.current_stream(dev)
+        main.wait_event(ev_pushed[s])
+        hps[s].replay()
+        ev_done[s].record(main)
+        side.wait_event(ev_done[s])
+        with torch.cuda.stream(side):
             ex.push(hps[s].rows, hps[s].meta, s)
             ex.wait(s)
             ex.release(s)
-            return s
+            ev_pushed[s].record(side)
+        state["i"] += 1
+
+    def drain():
+        """The timed region ends when the exchange of its last step has been delivered everywhere."""
+        if pipe is not None:
+            torch.cuda.current_stream(dev).wait_stream(side)
+            return (state["i"] - 1) & 1
         return None
 
     # clocks are sampled from here through the timed rounds and the per-kernel timing below
