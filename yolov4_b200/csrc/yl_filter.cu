@@ -1142,6 +1142,138 @@ k_filter_dense(const float *__restrict__ pred, long M, int C, int num_classes, f
     }
 }
 
+// Row-per-lane form of the dense front end (default).  A warp takes 32 consecutive rows -- 32 * (5+C) * 4 contiguous bytes, 16-byte
+// aligned when the first row index is a multiple of four -- as ONE bulk copy into its private shared-memory buffer (UBLKCP,
+// transaction mbarrier; the next batch is in flight while this one is walked), and every lane then walks ITS OWN row: the
+// reference's row filter is literally `obj * max_c cls >= conf` (utils.py:139-148), i.e. one NaN-propagating max chain
+// (FMNMX3.NAN, a class pitch of 5+C = 85 words is conflict-free) and one multiply-compare per row and lane, a quarter of the
+// instructions of the warp-per-row walk above, which spends a vote per row.  The ~8 % of rows that pass go through dense_row()
+// with all lanes, as before.
+constexpr int KR_ROWS = 32;
+
+__device__ __forceinline__ float max_nan(float a, float b)
+{
+    float d;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+    return d;
+}
+
+template <int NJ>
+__global__ void __launch_bounds__(320, 1)
+k_filter_dense_rows(const float *__restrict__ pred, long M, int C, int num_classes, float thr, int cap_seg,
+                    long row_first, long row_end, long rows_total, uint4 *__restrict__ cand, unsigned *__restrict__ seg_count)
+{
+    extern __shared__ __align__(128) unsigned char kr_smem[];
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    const int nch = 5 + C;
+    const int buf_floats = KR_ROWS * nch;                                      // a multiple of four floats
+    float *buf0 = reinterpret_cast<float *>(kr_smem) + (size_t)warp * 2 * buf_floats;
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(reinterpret_cast<float *>(kr_smem) + (size_t)n_warps * 2 * buf_floats) + 2 * warp;
+    if (lane == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    const long g_first = row_first / KR_ROWS, g_end = (row_end + KR_ROWS - 1) / KR_ROWS;
+    const long wid = (long)blockIdx.x * n_warps + warp, nw = (long)gridDim.x * n_warps;
+    // batch g = rows [32 g, 32 g + 32) of the tensor; the part of it inside the tensor arrives as one bulk copy (whole 16-byte
+    // units) plus at most three trailing floats by plain loads (tensor sizes that are not a multiple of four rows)
+    auto issue = [&](long g, int slot) {
+        const long r0 = g * KR_ROWS;
+        const long n_rows = min((long)KR_ROWS, rows_total - r0);
+        const unsigned bytes = (unsigned)(n_rows * nch * 4);
+        const unsigned bulk = bytes & ~15u;
+        float *dst = buf0 + (size_t)slot * buf_floats;
+        const float *src = pred + (size_t)r0 * nch;
+        if (lane == 0) {
+            mbar_expect_tx(&bar[slot], bulk);                                   // bulk == 0: the arrival alone completes the phase
+            if (bulk) bulk_g2s(dst, src, bulk, &bar[slot]);
+        }
+        const unsigned tail = (bytes - bulk) >> 2;
+        if ((unsigned)lane < tail) dst[(bulk >> 2) + lane] = src[(bulk >> 2) + lane];
+    };
+    long g = g_first + wid;
+    if (g < g_end) issue(g, 0);
+    unsigned it = 0;
+    while (g < g_end) {
+        const long gn = g + nw;
+        if (gn < g_end) issue(gn, (it + 1) & 1);                                // that buffer was walked in the previous iteration
+        mbar_wait(&bar[it & 1], (it >> 1) & 1u);
+        __syncwarp();                                                           // the tail floats of the plain loads
+        const float *buf = buf0 + (size_t)(it & 1) * buf_floats;
+        const long r0 = g * KR_ROWS;
+        const long row = r0 + lane;
+        const bool valid = row >= row_first && row < row_end;
+        bool pass = false;
+        if (valid) {
+            const float *rp = buf + lane * nch;
+            const float obj = rp[4];
+            float m0 = -kInf, m1 = -kInf, m2 = -kInf, m3 = -kInf;                // four chains: the max is associative
+            int k = 0;
+            for (; k + 4 <= num_classes; k += 4) {
+                m0 = max_nan(m0, rp[5 + k]); m1 = max_nan(m1, rp[6 + k]);
+                m2 = max_nan(m2, rp[7 + k]); m3 = max_nan(m3, rp[8 + k]);
+            }
+            for (; k < num_classes; ++k) m0 = max_nan(m0, rp[5 + k]);
+            const float m = max_nan(max_nan(m0, m1), max_nan(m2, m3));           // torch.max: NaN propagates (utils.py:139-141)
+            pass = __fmul_rn(obj, m) >= thr;                                     // :145  (NaN >= thr is False)
+        }
+        unsigned mask = __ballot_sync(FULL, pass);
+        while (mask) {
+            // The rows that passed the row filter (no NaN among their first num_classes classes, obj * max >= conf), four at a
+            // time so that the slot atomics of four rows are in flight together: one record per class column with
+            // obj * cls >= conf (utils.py:170 looks at every column >= 5), all lanes, lane = column mod 32.
+            int rrs[4];
+            int nq = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                rrs[q] = 0;
+                if (mask) { rrs[q] = __ffs(mask) - 1; mask &= mask - 1u; nq = q + 1; }
+            }
+            float e[4][NJ], obj[4];
+            unsigned slot[4][NJ], segb[4], rowi[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float *rp = buf + rrs[q] * nch;
+                obj[q] = rp[4];
+                const long r = r0 + rrs[q];
+                const unsigned b = (unsigned)(r / M);
+                rowi[q] = (unsigned)(r - (long)b * M);
+                segb[q] = b * (unsigned)C;
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) {
+                    const int idx = 32 * j + lane;
+                    e[q][j] = (q < nq && idx >= 5 && idx < nch) ? rp[idx] : __int_as_float(0x7FC00000);   // NaN never passes
+                    slot[q][j] = 0xFFFFFFFFu;
+                    if (__fmul_rn(e[q][j], obj[q]) >= thr) slot[q][j] = atomicAdd(&seg_count[segb[q] + (unsigned)(idx - 5)], 1u);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (q >= nq) break;
+                const float *rp = buf + rrs[q] * nch;
+                const float cx = rp[0], cy = rp[1], hw = __fmul_rn(rp[2], 0.5f), hh = __fmul_rn(rp[3], 0.5f);   // utils.py:117-126
+                const uint4 corners = make_uint4(__float_as_uint(__fsub_rn(cx, hw)), __float_as_uint(__fsub_rn(cy, hh)),
+                                                 __float_as_uint(__fadd_rn(cx, hw)), __float_as_uint(__fadd_rn(cy, hh)));
+#pragma unroll
+                for (int j = 0; j < NJ; ++j)
+                    if (slot[q][j] < (unsigned)cap_seg) {
+                        const int k = 32 * j + lane - 5;
+                        const float sc = __fadd_rn(__fmul_rn(obj[q], e[q][j]), 0.0f);       // nms score = obj*cls (utils.py:209)
+                        uint4 *rec = cand + ((size_t)(segb[q] + (unsigned)k) * cap_seg + slot[q][j]) * 2;
+                        rec[0] = make_uint4(__float_as_uint(sc), rowi[q], __float_as_uint(e[q][j]), __float_as_uint(obj[q]));
+                        rec[1] = corners;
+                    }
+            }
+        }
+        __syncwarp();                                                           // every lane has read the buffer
+        g = gn;
+        ++it;
+    }
+}
+
 // Fallback for a tensor whose base is not 16-byte aligned: one warp per row, scalar loads.
 __global__ void __launch_bounds__(KD_THREADS)
 k_filter_dense_unaligned(const float *__restrict__ pred, long M, int C, int num_classes, float thr, int cap_seg,
@@ -1434,6 +1566,39 @@ extern "C" int yl_filter_dense(const float *pred, int B, long M, int C, int num_
     const long row_first = (long)img_first * M, row_end = (long)(img_first + img_count) * M, rows_total = (long)B * M;
     uint4 *cand = (uint4 *)(w + L.off_cand);
     unsigned *seg_count = (unsigned *)(w + L.off_seg_count);
+    static const bool dense_groups = getenv("YL_DENSE") && strcmp(getenv("YL_DENSE"), "groups") == 0;   // the round-1 form, for A/B
+    const int nj = (5 + C + 31) / 32;
+    if (((uintptr_t)pred) % 16 == 0 && !dense_groups && nj <= KD_MAXJ) {
+        // row-per-lane form: 2 x 32 rows of shared memory per warp, as many warps per CTA as fit 200 KB, one CTA per SM
+        const size_t per_warp = (size_t)2 * KR_ROWS * (5 + C) * sizeof(float);
+        static const int max_warps = getenv("YL_KR_WARPS") ? atoi(getenv("YL_KR_WARPS")) : 8;
+        int warps = (int)((226 * 1024 - 256) / per_warp);
+        warps = warps > max_warps ? max_warps : warps;
+        if (warps >= 1) {
+            const size_t smem = per_warp * warps + 16 * (size_t)warps;
+            const long batches = (row_end + KR_ROWS - 1) / KR_ROWS - row_first / KR_ROWS;
+            const long ctas = (batches + warps - 1) / warps;
+            const int grid = (int)(ctas < g_num_sms() ? (ctas > 0 ? ctas : 1) : g_num_sms());
+            cudaStream_t st = (cudaStream_t)stream;
+            switch (nj) {
+#define YL_KR_CASE(NJ_)                                                                                               \
+    case NJ_: {                                                                                                       \
+        static size_t attr_smem = 0;                                                                                  \
+        if (smem > attr_smem) {                                                                                       \
+            YL_CUDA_TRY(cudaFuncSetAttribute(k_filter_dense_rows<NJ_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            attr_smem = smem;                                                                                         \
+        }                                                                                                             \
+        k_filter_dense_rows<NJ_><<<grid, 32 * warps, smem, st>>>(pred, M, C, num_classes, conf_thre, cap_seg, row_first, row_end, \
+                                                                 rows_total, cand, seg_count);                        \
+    } break;
+                YL_KR_CASE(1) YL_KR_CASE(2) YL_KR_CASE(3) YL_KR_CASE(4)
+            default: YL_KR_CASE(KD_MAXJ)
+#undef YL_KR_CASE
+            }
+            YL_LAUNCH_CHECK();
+            return YL_OK;
+        }
+    }
     if (((uintptr_t)pred) % 16 == 0) {
         const long warps_needed = ((row_end - row_first) / 4 + KD_GROUPS) / KD_GROUPS;
         const long blocks_needed = (warps_needed + KD_WARPS - 1) / KD_WARPS;
