@@ -482,6 +482,60 @@ def main():
                 "parity_checked_ranks_on_rank0": checked, "parity": "gathered rows == recomputed shards, bit-exact, on every rank",
                 "status": ex.status()}
 
+    # ---- BASELINE config 5 at N>1: batch 1024 sharded by image over the ranks, exchange included ---------------------------
+    config5 = None
+    if world > 1 and 1024 % world == 0 and not args.no_extras:
+        B5 = 1024 // world
+        raws5 = synth_head_outputs(B5, IMG, C, seed=100 + rank, device=dev)
+        hps5 = [yb.HeadPostprocessor(B5, GRIDS, C, CONF, NMS, device=dev).capture(raws5) for _ in range(2)]
+        rows5 = sum(0 if r is None else r.shape[0] for r in hps5[0].results())
+        ex5 = DetectionExchange(B5, hps5[0].cap_out, dev, slots=2)
+        evd = [torch.cuda.Event(), torch.cuda.Event()]
+        evp = [torch.cuda.Event(), torch.cuda.Event()]
+        for e in evp:
+            e.record()
+
+        def step5(i):
+            s5 = i & 1
+            main = torch.cuda.current_stream(dev)
+            main.wait_event(evp[s5])
+            hps5[s5].replay()
+            evd[s5].record(main)
+            side.wait_event(evd[s5])
+            with torch.cuda.stream(side):
+                ex5.push(hps5[s5].rows, hps5[s5].meta, s5)
+                ex5.wait(s5)
+                ex5.release(s5)
+                evp[s5].record(side)
+
+        n5 = max(4, min(args.steps, 20))
+        for i in range(4):
+            step5(i)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        barrier()
+        ev0.record()
+        for i in range(n5):
+            step5(i)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        ev1.record()
+        barrier()
+        sec5 = ev0.elapsed_time(ev1) / 1e3
+        t = torch.tensor([sec5], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sec5 = float(t.item())
+        got5 = ex5.results((n5 - 1) & 1)
+        ok5 = rows_equal(got5[rank * B5:(rank + 1) * B5], hps5[0].results())
+        flag = torch.tensor([0 if ok5 else 1], device=dev)
+        dist.all_reduce(flag)
+        if int(flag.item()) != 0:
+            raise SystemExit("config 5: exchanged rows differ from the local rows")
+        config5 = {"workload": "batch 1024 @608 conf 1e-4 nms 0.4 sharded by image: %d images per GPU, exchange of all detections included" % B5,
+                   "images_per_s": 1024 * n5 / sec5, "ms_per_step": 1e3 * sec5 / n5, "steps": n5, "rows_per_step_this_rank": rows5,
+                   "nvlink_out_gbs_per_rank": (world - 1) * rows5 * 28 / (sec5 / n5) / 1e9, "status": ex5.status()}
+        ex5.close()
+        del hps5, raws5
+        torch.cuda.empty_cache()
+
     # ---- roofline: the dominant kernel alone, CUDA events on its stream ----------------------------------------------------
     L = _cabi.lib()
     st = torch.cuda.current_stream().cuda_stream
@@ -607,7 +661,7 @@ def main():
             "cpu_baseline": cpu,
             "parity": parity,
             "exchange": xchg,
-            "extra": extra,
+            "extra": extra if extra is not None else ({"config5_b1024_sharded": config5} if config5 else None),
             "clocks": clocks,
         }
         emit(line)
