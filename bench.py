@@ -460,7 +460,8 @@ def main():
         rps = torch.tensor([rows_per_step], device=dev, dtype=torch.int64)
         dist.all_reduce(rps)
         rows_all_ranks = int(rps.item())
-        bytes_out = (world - 1) * (rows_per_step * 28 + B * 4)               # this rank's peer stores per step
+        bytes_in = (world - 1) * (rows_per_step * 28 + B * 4)                # what reaches this rank per step (every form)
+        bytes_out = bytes_in if "multicast" not in ex.mode else rows_per_step * 28 + B * 4    # multicast: the switch replicates
         # parity: the gathered rows of two other ranks' shards, recomputed on this GPU from their seeds, bit for bit
         got = ex.results(last_slot)
         checked = []
@@ -474,11 +475,13 @@ def main():
         dist.all_reduce(flag)
         if int(flag.item()) != 0:
             raise SystemExit("exchange parity FAILED: gathered rows differ from the recomputed shards")
-        xchg = {"kind": "peer stores over NVLink into every rank's window (yl_xchg_push/wait/release, CUDA IPC), exchange of step i "
-                        "under the kernels of step i+1, counts stay on the device",
+        xchg = {"kind": "%s (yl_xchg_push/wait/release), exchange of step i under the kernels of step i+1, counts stay on the "
+                        "device" % ex.mode,
                 "value_without_exchange": world * B * args.steps / sec_nox, "ms_per_step_without_exchange": 1e3 * sec_nox / args.steps,
-                "nvlink_bytes_out_per_rank_per_step": bytes_out, "rows_per_step_all_ranks": rows_all_ranks,
+                "nvlink_bytes_out_per_rank_per_step": bytes_out, "nvlink_bytes_in_per_rank_per_step": bytes_in,
+                "rows_per_step_all_ranks": rows_all_ranks,
                 "nvlink_out_gbs_per_rank": bytes_out / (sec / args.steps) / 1e9,
+                "nvlink_in_gbs_per_rank": bytes_in / (sec / args.steps) / 1e9,
                 "parity_checked_ranks_on_rank0": checked, "parity": "gathered rows == recomputed shards, bit-exact, on every rank",
                 "status": ex.status()}
 

@@ -234,6 +234,14 @@ int yl_detect_host(yl_context *ctx, const float *const *raw_host, float conf_thr
 typedef struct yl_xchg yl_xchg;
 int yl_xchg_create(yl_xchg **out, int device, int rank, int world, int B, long cap_out, int slots);
 int yl_xchg_destroy(yl_xchg *x);
+/* The same object over windows the CALLER owns: `windows[p]` = rank p's window as mapped into this process (all of
+ * yl_xchg_window_bytes() bytes, 256-byte aligned; e.g. torch symmetric memory), `multicast` = an NVSwitch multicast mapping of the
+ * same windows or NULL.  With a multicast mapping yl_xchg_push issues ONE multimem.st per 16 bytes and the switch replicates it into
+ * every window (a rank sends 1/world of the peer-store forms' bytes).  No CUDA IPC; yl_xchg_destroy leaves the windows alone.
+ * The caller synchronises the ranks between creation and the first push. */
+size_t yl_xchg_window_bytes(int world, int B, long cap_out, int slots);
+int yl_xchg_create_external(yl_xchg **out, int device, int rank, int world, int B, long cap_out, int slots,
+                            void *const *windows, void *multicast);
 size_t yl_xchg_handle_bytes(void);
 int yl_xchg_local_handle(yl_xchg *x, void *handle);
 int yl_xchg_connect(yl_xchg *x, const void *handles);

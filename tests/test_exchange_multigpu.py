@@ -30,16 +30,20 @@ def _detect(seed, dev):
     return hp, rows, meta
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, backend="gloo"):
     try:
         os.environ["MASTER_ADDR"] = "127.0.0.1"
         os.environ["MASTER_PORT"] = str(port)
         dev = torch.device("cuda", rank)
         torch.cuda.set_device(dev)
         if world > 1:
-            dist.init_process_group("gloo", rank=rank, world_size=world)
+            if backend == "nccl":
+                dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+            else:
+                dist.init_process_group("gloo", rank=rank, world_size=world)
         from yolov4_b200.sharded import DetectionExchange
         ex = DetectionExchange(B, CAP, dev, slots=2)
+        mode = ex.mode
         ok, n_rows, first_bad = True, 0, ""
         for step in range(STEPS):
             slot = step % 2
@@ -76,25 +80,26 @@ def _worker(rank, world, port, q):
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
-        q.put((rank, bool(ok), n_rows, first_bad, ))
+        q.put((rank, bool(ok), n_rows, first_bad + " [" + mode + "]"))
     except Exception as e:                                        # pragma: no cover
         q.put((rank, False, repr(e)))
 
 
-def _run(world):
+def _run(world, backend="gloo"):
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, backend)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted(q.get(timeout=300) for _ in procs)
     for p in procs:
         p.join(timeout=60)
     assert all(r[1] for r in res), res
+    return res
 
 
 def test_exchange_single_rank_self_window():
@@ -114,3 +119,11 @@ def test_exchange_two_ranks_bit_exact_over_reused_slots():
 @pytest.mark.skipif(torch.cuda.device_count() < 4, reason="needs four GPUs")
 def test_exchange_four_ranks_bit_exact_over_reused_slots():
     _run(4)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+def test_exchange_two_ranks_multicast_or_its_fallback():
+    """With an NCCL group the windows live in torch symmetric memory and the push is one multimem.st per 16 bytes (NVSwitch
+    multicast); where the platform has no multicast mapping every rank falls back to the CUDA IPC windows.  Either way: bit-exact."""
+    res = _run(2, backend="nccl")
+    print("exchange mode:", res[0][3])

@@ -9,7 +9,9 @@ B = 64
 hps = []
 for seed in (0, 1):
     raws = synth_head_outputs(B, 608, 80, seed=seed, device="cuda")
-    hps.append(yb.HeadPostprocessor(B, [76, 38, 19], 80, 1e-4, 0.4).capture(raws))
+    hp = yb.HeadPostprocessor(B, [76, 38, 19], 80, 1e-4, 0.4)
+    hp.ws.buf.zero_()                      # (diagnostic builds that skip a scale leave its flag words untouched)
+    hps.append(hp.capture(raws))
 N = 200
 def run(streams):
     for it in range(N):

@@ -91,6 +91,10 @@ def lib():
     L.yl_detect_host.argtypes = [_p, _p, _f, _f, _p, _p]
     L.yl_xchg_create.restype = _i
     L.yl_xchg_create.argtypes = [ctypes.POINTER(_p), _i, _i, _i, _i, _l, _i]
+    L.yl_xchg_window_bytes.restype = _sz
+    L.yl_xchg_window_bytes.argtypes = [_i, _i, _l, _i]
+    L.yl_xchg_create_external.restype = _i
+    L.yl_xchg_create_external.argtypes = [ctypes.POINTER(_p), _i, _i, _i, _i, _l, _i, _p, _p]
     L.yl_xchg_destroy.restype = _i
     L.yl_xchg_destroy.argtypes = [_p]
     L.yl_xchg_handle_bytes.restype = _sz
@@ -121,7 +125,7 @@ EXPORTS = [
     "yl_post_workspace_bytes", "yl_post_reset", "yl_filter_raw", "yl_filter_raw_stage", "yl_filter_dense", "yl_nms", "yl_build_target", "yl_build_target3", "yl_coco_rows", "yl_coco_rows_padded",
     "yl_loss_forward", "yl_loss_forward_chained", "yl_loss_backward",
     "yl_context_create", "yl_context_destroy", "yl_detect_host",
-    "yl_xchg_create", "yl_xchg_destroy", "yl_xchg_handle_bytes", "yl_xchg_local_handle", "yl_xchg_connect", "yl_xchg_push",
+    "yl_xchg_create", "yl_xchg_create_external", "yl_xchg_window_bytes", "yl_xchg_destroy", "yl_xchg_handle_bytes", "yl_xchg_local_handle", "yl_xchg_connect", "yl_xchg_push",
     "yl_xchg_wait", "yl_xchg_release", "yl_xchg_rows", "yl_xchg_counts", "yl_xchg_status",
 ]
 

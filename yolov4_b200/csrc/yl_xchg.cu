@@ -151,13 +151,22 @@ k_xchg_push(const __grid_constant__ XchgPeers P, int rank, int world, int B, lon
 // XB_BYTES (SASS UBLKCP), issued by ONE thread per CTA over a ring of XB_STAGES shared-memory stages.  No register staging, no
 // per-thread 16-byte stores: the copy engines of the SM (TMA) produce large NVLink write bursts while the CTA's other warps do not
 // exist at all (32 threads per CTA), so the push takes almost nothing from the step's kernels it runs next to.
+__device__ __forceinline__ void mc_st4(float *mc, const float4 &v)
+{
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void mc_st1(unsigned *mc, unsigned v)
+{
+    asm volatile("multimem.st.relaxed.sys.global.u32 [%0], %1;" ::"l"(mc), "r"(v) : "memory");
+}
+
 constexpr unsigned XB_BYTES = 16384;
 constexpr int XB_STAGES = 4;
 
 __device__ __forceinline__ unsigned xb_smem(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
 __global__ void __launch_bounds__(32)
-k_xchg_push_bulk(const __grid_constant__ XchgPeers P, int rank, int world, int B, long cap_out, int slots, int slot,
+k_xchg_push_bulk(const __grid_constant__ XchgPeers P, XchgWindow mc, int rank, int world, int B, long cap_out, int slots, int slot,
                  const float *__restrict__ rows, const int *__restrict__ counts, unsigned *__restrict__ done,
                  int *__restrict__ status, unsigned long long limit_ns)
 {
@@ -205,9 +214,14 @@ k_xchg_push_bulk(const __grid_constant__ XchgPeers P, int rank, int world, int B
                              : "=r"(ok) : "r"(xb_smem(&bar[s])), "r"(parity) : "memory");
             } while (!ok);
             const size_t dst_off = (((size_t)slot * world * B + (size_t)rank * B + b)) * img_bytes + lo;
-            for (int p = 0; p < world; ++p) {
-                char *dst = reinterpret_cast<char *>(P.w[p].rows) + dst_off;
+            if (mc.rows) {                                             // multicast mapping: one bulk store, the switch replicates
+                char *dst = reinterpret_cast<char *>(mc.rows) + dst_off;
                 asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(dst_s), "r"(len) : "memory");
+            } else {
+                for (int p = 0; p < world; ++p) {
+                    char *dst = reinterpret_cast<char *>(P.w[p].rows) + dst_off;
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(dst_s), "r"(len) : "memory");
+                }
             }
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             ++it;
@@ -217,7 +231,9 @@ k_xchg_push_bulk(const __grid_constant__ XchgPeers P, int rank, int world, int B
     // counts (a few bytes per image) by plain stores
     for (int b = blockIdx.x * 32 + threadIdx.x; b < B; b += gridDim.x * 32) {
         const int n = min(max(counts[b], 0), (int)cap_out);
-        for (int p = 0; p < world; ++p) P.w[p].counts[(size_t)slot * world * B + (size_t)rank * B + b] = n;
+        const size_t ci = (size_t)slot * world * B + (size_t)rank * B + b;
+        if (mc.rows) mc_st1(reinterpret_cast<unsigned *>(mc.counts) + ci, (unsigned)n);
+        else for (int p = 0; p < world; ++p) P.w[p].counts[ci] = n;
     }
     __syncwarp();
     if (threadIdx.x == 0) {
@@ -229,7 +245,69 @@ k_xchg_push_bulk(const __grid_constant__ XchgPeers P, int rank, int world, int B
     if (sh_ok == 2) {
         if (threadIdx.x == 0) done[slot] = 0u;
         __threadfence_system();
-        if (threadIdx.x < world) st_sys(P.w[threadIdx.x].flag + slot * XCHG_MAX_WORLD + rank, epoch + 1u);
+        if (mc.rows) { if (threadIdx.x == 0) mc_st1(mc.flag + slot * XCHG_MAX_WORLD + rank, epoch + 1u); }
+        else if (threadIdx.x < world) st_sys(P.w[threadIdx.x].flag + slot * XCHG_MAX_WORLD + rank, epoch + 1u);
+    }
+}
+
+// ---- NVSwitch multicast form of the push: the window lives in symmetric memory with a multicast mapping (torch's symmetric
+// memory does the CUDA VMM / fabric plumbing); ONE multimem.st per 16 bytes reaches every rank's window, the switch replicates.
+// A rank then sends 1/world of what the peer-store forms send; what arrives is unchanged.
+__global__ void __launch_bounds__(XCHG_THREADS)
+k_xchg_push_mc(const __grid_constant__ XchgPeers P, XchgWindow mc, int rank, int world, int B, long cap_out, int slots, int slot,
+               const float *__restrict__ rows, const int *__restrict__ counts, unsigned *__restrict__ done,
+               int *__restrict__ status, unsigned long long limit_ns)
+{
+    __shared__ unsigned sh_epoch;
+    __shared__ int sh_ok;
+    const XchgWindow &me = P.w[rank];
+    if (threadIdx.x == 0) { sh_epoch = me.epoch[slot]; sh_ok = 1; }
+    __syncthreads();
+    const unsigned epoch = sh_epoch;
+    if (threadIdx.x < world && !spin_ge(me.ack + slot * XCHG_MAX_WORLD + threadIdx.x, epoch, limit_ns)) sh_ok = 0;
+    __syncthreads();
+    if (!sh_ok) {
+        if (threadIdx.x == 0) atomicExch(status, 1);
+        return;
+    }
+    const size_t img_f4 = (size_t)cap_out * 7 / 4;
+    const int n_chunks = (int)((img_f4 + XCHG_CHUNK - 1) / XCHG_CHUNK);
+    for (int u = blockIdx.x; u < B * n_chunks; u += gridDim.x) {
+        const int b = u / n_chunks, c = u - b * n_chunks;
+        const int n = min(max(counts[b], 0), (int)cap_out);
+        const unsigned nf4 = ((unsigned)n * 7u + 3u) >> 2;
+        const unsigned lo = (unsigned)c * XCHG_CHUNK;
+        const size_t dst_img = ((size_t)slot * world * B + (size_t)rank * B + b);
+        if (c == 0 && threadIdx.x == 0) mc_st1(reinterpret_cast<unsigned *>(mc.counts) + dst_img, (unsigned)n);
+        if (lo >= nf4) continue;
+        const unsigned hi = min(nf4, lo + XCHG_CHUNK);
+        const float4 *src = reinterpret_cast<const float4 *>(rows) + (size_t)b * img_f4;
+        for (unsigned i0 = lo + threadIdx.x; i0 < hi; i0 += XCHG_THREADS * XCHG_UNROLL) {
+            float4 v[XCHG_UNROLL];
+#pragma unroll
+            for (int k = 0; k < XCHG_UNROLL; ++k) {
+                const unsigned i = i0 + k * XCHG_THREADS;
+                if (i < hi) v[k] = src[i];
+            }
+#pragma unroll
+            for (int k = 0; k < XCHG_UNROLL; ++k) {
+                const unsigned i = i0 + k * XCHG_THREADS;
+                if (i < hi) mc_st4(mc.rows + (dst_img * img_f4 + i) * 4, v[k]);
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        sh_ok = (atomicAdd(done + slot, 1u) == gridDim.x - 1) ? 2 : 1;
+    }
+    __syncthreads();
+    if (sh_ok == 2) {
+        if (threadIdx.x == 0) {
+            done[slot] = 0u;
+            __threadfence_system();
+            mc_st1(mc.flag + slot * XCHG_MAX_WORLD + rank, epoch + 1u);      // one store raises this source's flag everywhere
+        }
     }
 }
 
@@ -265,7 +343,9 @@ struct yl_xchg {
     char *peer[XCHG_MAX_WORLD];        // mapped windows (peer[rank] == window)
     XchgPeers P;
     unsigned long long limit_ns;
-    bool connected, bulk;
+    bool connected, bulk, external;    // external: the windows belong to the caller (symmetric memory), not to this object
+    char *mc;                          // multicast mapping of the windows, or null
+    XchgWindow MC;
 };
 
 static XchgWindow window_of(char *base, const XchgLayout &L)
@@ -283,9 +363,11 @@ extern "C" int yl_xchg_destroy(yl_xchg *x)
 {
     if (!x) return YL_OK;
     cudaSetDevice(x->device);
-    for (int p = 0; p < x->world; ++p)
-        if (p != x->rank && x->peer[p]) cudaIpcCloseMemHandle(x->peer[p]);
-    if (x->window) cudaFree(x->window);
+    if (!x->external) {
+        for (int p = 0; p < x->world; ++p)
+            if (p != x->rank && x->peer[p]) cudaIpcCloseMemHandle(x->peer[p]);
+        if (x->window) cudaFree(x->window);
+    }
     free(x);
     return YL_OK;
 }
@@ -310,6 +392,45 @@ extern "C" int yl_xchg_create(yl_xchg **out, int device, int rank, int world, in
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { yl_xchg_destroy(x); return YL_ERR_CUDA_BASE + (int)e; }
     x->peer[rank] = x->window;
+    *out = x;
+    return YL_OK;
+}
+
+extern "C" size_t yl_xchg_window_bytes(int world, int B, long cap_out, int slots)
+{
+    if (world < 1 || world > XCHG_MAX_WORLD || B <= 0 || cap_out <= 0 || cap_out % 4 != 0 || slots < 1 || slots > 8) return 0;
+    return xchg_layout(world, B, cap_out, slots).total;
+}
+
+extern "C" int yl_xchg_create_external(yl_xchg **out, int device, int rank, int world, int B, long cap_out, int slots,
+                                       void *const *windows, void *multicast)
+{
+    if (!out || !windows || rank < 0 || world < 1 || world > XCHG_MAX_WORLD || rank >= world || B <= 0 || cap_out <= 0 ||
+        cap_out % 4 != 0 || slots < 1 || slots > 8)
+        return YL_ERR_ARG;
+    for (int p = 0; p < world; ++p)
+        if (!windows[p] || ((uintptr_t)windows[p]) % 256 != 0) return YL_ERR_ARG;
+    yl_xchg *x = (yl_xchg *)calloc(1, sizeof(yl_xchg));
+    if (!x) return YL_ERR_ARG;
+    x->device = device; x->rank = rank; x->world = world; x->B = B; x->cap_out = cap_out; x->slots = slots;
+    x->L = xchg_layout(world, B, cap_out, slots);
+    x->limit_ns = 5000000000ull;
+    // through the multicast mapping a rank sends 1/world of the bytes: 16 single-warp CTAs keep the switch busy (8 GPUs: 267 us per
+    // step with 16, 273 us with 64), the peer-store forms want 64
+    x->push_ctas = getenv("YL_XCHG_CTAS") ? atoi(getenv("YL_XCHG_CTAS")) : (multicast ? 16 : 64);
+    if (x->push_ctas < 1) x->push_ctas = 1;
+    x->bulk = !(getenv("YL_XCHG_BULK") && getenv("YL_XCHG_BULK")[0] == '0');
+    x->external = true;
+    for (int p = 0; p < world; ++p) { x->peer[p] = (char *)windows[p]; x->P.w[p] = window_of(x->peer[p], x->L); }
+    x->window = x->peer[rank];
+    x->mc = (char *)multicast;
+    if (x->mc) x->MC = window_of(x->mc, x->L);
+    cudaError_t e = cudaSetDevice(device);
+    // flags, acks, epochs, counters of THIS rank's window start at zero (the caller synchronises the ranks before the first push)
+    if (e == cudaSuccess) e = cudaMemset(x->window + x->L.off_counts, 0, x->L.total - x->L.off_counts);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { free(x); return YL_ERR_CUDA_BASE + (int)e; }
+    x->connected = true;
     *out = x;
     return YL_OK;
 }
@@ -348,6 +469,13 @@ extern "C" int yl_xchg_push(yl_xchg *x, const float *rows, const int *counts, in
     if (!x || !rows || !counts || slot < 0 || slot >= x->slots || !x->connected) return YL_ERR_ARG;
     if (((uintptr_t)rows) % 16 != 0) return YL_ERR_ARG;
     const int grid = x->push_ctas;
+    if (x->mc && !x->bulk) {
+        k_xchg_push_mc<<<grid, XCHG_THREADS, 0, (cudaStream_t)stream>>>(x->P, x->MC, x->rank, x->world, x->B, x->cap_out, x->slots, slot, rows,
+                                                                        counts, (unsigned *)(x->window + x->L.off_done),
+                                                                        (int *)(x->window + x->L.off_status), x->limit_ns);
+        YL_LAUNCH_CHECK();
+        return YL_OK;
+    }
     if (x->bulk) {
         static bool attr_done = false;
         const int smem = XB_STAGES * (int)XB_BYTES;
@@ -355,7 +483,9 @@ extern "C" int yl_xchg_push(yl_xchg *x, const float *rows, const int *counts, in
             YL_CUDA_TRY(cudaFuncSetAttribute(k_xchg_push_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             attr_done = true;
         }
-        k_xchg_push_bulk<<<grid, 32, smem, (cudaStream_t)stream>>>(x->P, x->rank, x->world, x->B, x->cap_out, x->slots, slot, rows, counts,
+        XchgWindow mcw = x->MC;
+        if (!x->mc) mcw.rows = nullptr;
+        k_xchg_push_bulk<<<grid, 32, smem, (cudaStream_t)stream>>>(x->P, mcw, x->rank, x->world, x->B, x->cap_out, x->slots, slot, rows, counts,
                                                                    (unsigned *)(x->window + x->L.off_done),
                                                                    (int *)(x->window + x->L.off_status), x->limit_ns);
         YL_LAUNCH_CHECK();

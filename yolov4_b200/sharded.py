@@ -51,8 +51,9 @@ class DetectionExchange:
 
     torch.distributed is used once, for the 64-byte handles; NCCL moves no detection.  world == 1 works (self window)."""
 
-    def __init__(self, b_local, cap_out, device, slots=2, group=None):
+    def __init__(self, b_local, cap_out, device, slots=2, group=None, multicast="auto"):
         import ctypes
+        import os
 
         import numpy as np
         from . import _cabi
@@ -62,7 +63,13 @@ class DetectionExchange:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.h = ctypes.c_void_p()
+        self._views = {}
         dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.mode = "peer stores into CUDA IPC windows"
+        if multicast == "auto":
+            multicast = os.environ.get("YL_XCHG_MC", "1") != "0"
+        if multicast and self.world > 1 and dist.get_backend(group) == "nccl" and self._try_multicast(dev_index, group):
+            return
         _cabi.check(self.L.yl_xchg_create(ctypes.byref(self.h), dev_index, self.rank, self.world, self.B, self.cap_out, self.slots))
         nb = int(self.L.yl_xchg_handle_bytes())
         mine = (ctypes.c_ubyte * nb)()
@@ -78,7 +85,36 @@ class DetectionExchange:
         _cabi.check(self.L.yl_xchg_connect(self.h, buf))
         if self.world > 1:
             dist.barrier(group=group)                      # every window is mapped before anybody pushes
-        self._views = {}
+
+    def _try_multicast(self, dev_index, group):
+        """Windows in torch symmetric memory with an NVSwitch multicast mapping: yl_xchg_push then issues one multimem.st per 16
+        bytes and the switch replicates it (a rank sends 1/world of the bytes).  torch only allocates and maps the memory; the
+        kernels are the library's.  All ranks agree on the outcome; any failure falls back to the CUDA IPC windows."""
+        import ctypes
+        ok, ptrs, mc = 1, None, 0
+        try:
+            import torch.distributed._symmetric_memory as symm
+            nbytes = int(self.L.yl_xchg_window_bytes(self.world, self.B, self.cap_out, self.slots))
+            self._symm_buf = symm.empty(nbytes, dtype=torch.uint8, device=self.device)
+            hdl = symm.rendezvous(self._symm_buf, dist.group.WORLD if group is None else group)
+            ptrs = [int(p) for p in hdl.buffer_ptrs]
+            mc = int(hdl.multicast_ptr or 0)
+            if mc == 0 or len(ptrs) != self.world:
+                ok = 0
+            self._symm_hdl = hdl
+        except Exception:
+            ok = 0
+        flag = torch.tensor([ok], device=self.device, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag.item()) == 0:
+            self._symm_buf = self._symm_hdl = None
+            return False
+        arr = (ctypes.c_void_p * self.world)(*ptrs)
+        self._cabi.check(self.L.yl_xchg_create_external(ctypes.byref(self.h), dev_index, self.rank, self.world, self.B, self.cap_out,
+                                                         self.slots, arr, ctypes.c_void_p(mc)))
+        dist.barrier(group=group)                          # every window's flags are zero before anybody pushes
+        self.mode = "NVSwitch multicast (multimem.st) into symmetric-memory windows"
+        return True
 
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
