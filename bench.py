@@ -534,7 +534,7 @@ def main():
             raise SystemExit("config 5: exchanged rows differ from the local rows")
         config5 = {"workload": "batch 1024 @608 conf 1e-4 nms 0.4 sharded by image: %d images per GPU, exchange of all detections included" % B5,
                    "images_per_s": 1024 * n5 / sec5, "ms_per_step": 1e3 * sec5 / n5, "steps": n5, "rows_per_step_this_rank": rows5,
-                   "nvlink_out_gbs_per_rank": (world - 1) * rows5 * 28 / (sec5 / n5) / 1e9, "status": ex5.status()}
+                   "nvlink_in_gbs_per_rank": (world - 1) * rows5 * 28 / (sec5 / n5) / 1e9, "exchange": ex5.mode, "status": ex5.status()}
         ex5.close()
         del hps5, raws5
         torch.cuda.empty_cache()
