@@ -34,7 +34,8 @@ METRIC = "images/sec decode+NMS @608 b64 conf1e-4"
 UNIT = "images/s"
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel at B=64, from the ncu --set full captures
 # under profiles/ (per front-end form; the live frac_physical below divides these by the launch time measured in this run)
-TRAFFIC_PER_LAUNCH = {"k_flag_raw": 475235072 + 10179328}               # profiles/r1_k_flag_raw_ncu_full_raw.csv
+TRAFFIC_PER_LAUNCH = {"k_flag_raw": 475289856 + 9423360,                # profiles/r2_k_flag_raw_ncu_full_details.txt
+                      "k_flag_tma": 472751104 + 4560896}                # profiles/r2_k_flag_tma_ncu_full_details.txt
 WORKLOAD = "yolov4 head outputs batch %d/GPU @608x608 (grids 76/38/19), 80 classes, conf 1e-4, nms 0.4 (BASELINE configs[1])"
 
 
@@ -326,6 +327,9 @@ def main():
     ap.add_argument("--min-seconds", type=float, default=0.25, help="the K-step timed region is repeated until this much device "
                                                                     "time is covered; the line reports the median round")
     ap.add_argument("--no-extras", action="store_true", help="skip the other configs' numbers")
+    ap.add_argument("--inflight", type=int, default=3, help="steps in flight: each step's chain is a CUDA graph; step i runs on stream "
+                                                            "i %% inflight with its own workspace and output rows, so the latency-bound "
+                                                            "kernels of a step run under the streaming pass of the next ones (1 = serial)")
     args = ap.parse_args()
     claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
@@ -349,10 +353,12 @@ def main():
     B = args.batch
     sampler = ClockSampler(local_rank) if rank == 0 else None   # nvidia-smi needs ~0.3 s before its first sample
     raws = synth_head_outputs(B, IMG, C, seed=rank, device=dev)
-    # Two postprocessors (own output rows and workspace each, the same inputs): step i writes rows[i % 2] while the exchange of step
-    # i-1 still reads rows[(i-1) % 2].  On one GPU only the first is used.
-    n_hp = 2 if world > 1 else 1
-    hps = [yb.HeadPostprocessor(B, GRIDS, C, CONF, NMS, device=dev, n_groups=args.groups).capture(raws) for _ in range(n_hp)]
+    # NP postprocessors (own workspace, output rows and CUDA graph each, the same read-only inputs), one per step in flight
+    NP = max(1, min(int(args.inflight), 8))
+    if world > 1:
+        NP = max(NP, 2)                                  # the exchange of step i reads rows[i % NP] while step i+1 runs
+    hps = [yb.HeadPostprocessor(B, GRIDS, C, CONF, NMS, device=dev, n_groups=args.groups).capture(raws) for _ in range(NP)]
+    cstreams = [torch.cuda.Stream(device=dev) for _ in range(NP)]
     hp = hps[0]
     res = hp.results()                                   # validates capacities; also the first parity-visible output
     rows_per_step = sum(0 if r is None else r.shape[0] for r in res)
@@ -361,10 +367,10 @@ def main():
     pipe = None
     if world > 1:
         from yolov4_b200.sharded import DetectionExchange
-        ex = DetectionExchange(B, hp.cap_out, dev, slots=2)
+        ex = DetectionExchange(B, hp.cap_out, dev, slots=NP)
         side = torch.cuda.Stream(device=dev, priority=int(os.environ.get("YL_XCHG_PRIO", "0")))
-        ev_done = [torch.cuda.Event(), torch.cuda.Event()]
-        ev_pushed = [torch.cuda.Event(), torch.cuda.Event()]
+        ev_done = [torch.cuda.Event() for _ in range(NP)]
+        ev_pushed = [torch.cuda.Event() for _ in range(NP)]
         for e in ev_pushed:
             e.record()
         pipe = True
@@ -377,33 +383,45 @@ def main():
     state = {"i": 0}
 
     def step():
-        """One step.  At N>1: the chain of step i (CUDA graph, into rows[i % 2]) on the main stream; its exchange (push the kept rows
-        into every rank's window over NVLink, wait for everybody's rows of that slot, release it) follows on the side stream and
-        runs under the chain of step i+1; the chain of step i+2 waits for it before it overwrites rows[i % 2]."""
-        if pipe is None:
-            hp.replay()
-            return
-        s = state["i"] & 1
-        main = torch.cuda.current_stream(dev)
-        main.wait_event(ev_pushed[s])
-        hps[s].replay()
-        ev_done[s].record(main)
-        side.wait_event(ev_done[s])
-        with torch.cuda.stream(side):
-            ex.push(hps[s].rows, hps[s].meta, s)
-            ex.wait(s)
-            ex.release(s)
-            ev_pushed[s].record(side)
+        """One step = the chain of one batch (a CUDA graph), on stream i % NP with postprocessor i % NP: NP steps are in flight, so the
+        emit / NMS / gather kernels of a step run under the streaming pass of the following ones.  At N>1 the step's exchange (push
+        the kept rows into every rank's window, wait for everybody's rows of that slot, release it) follows on the side stream,
+        and the step that reuses rows[i % NP] waits for it."""
+        p = state["i"] % NP
+        cs = cstreams[p]
+        if pipe is not None:
+            cs.wait_event(ev_pushed[p])
+        with torch.cuda.stream(cs):
+            hps[p].replay()
+            if pipe is not None:
+                ev_done[p].record(cs)
+        if pipe is not None:
+            side.wait_event(ev_done[p])
+            with torch.cuda.stream(side):
+                ex.push(hps[p].rows, hps[p].meta, p)
+                ex.wait(p)
+                ex.release(p)
+                ev_pushed[p].record(side)
         state["i"] += 1
 
+    def begin():
+        """The streams of the pipeline start behind everything enqueued on the current stream (the start event of a timed round)."""
+        cur = torch.cuda.current_stream(dev)
+        for cs in cstreams:
+            cs.wait_stream(cur)
+
     def drain():
-        """The timed region ends when the exchange of its last step has been delivered everywhere."""
+        """The timed region ends when every step in flight has finished and (N>1) its exchange has been delivered everywhere."""
+        cur = torch.cuda.current_stream(dev)
+        for cs in cstreams:
+            cur.wait_stream(cs)
         if pipe is not None:
-            torch.cuda.current_stream(dev).wait_stream(side)
-            return (state["i"] - 1) & 1
+            cur.wait_stream(side)
+            return (state["i"] - 1) % NP
         return None
 
     # clocks are sampled from here through the timed rounds and the per-kernel timing below
+    begin()
     for _ in range(args.warmup):
         step()
     drain()
@@ -414,6 +432,7 @@ def main():
         state["i"] = 0
         barrier()
         ev0.record()
+        begin()
         for _ in range(args.steps):
             step()
         last = drain()
@@ -441,18 +460,35 @@ def main():
     sec = float(np.median(rounds))
     value = world * B * args.steps / sec
 
+    # ---- one step alone (serial replays of one graph): the latency of a step, next to the pipelined throughput above --------
+    for _ in range(3):
+        hp.replay()
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        hp.replay()
+    ev1.record()
+    barrier()
+    sec_serial = ev0.elapsed_time(ev1) / 1e3
+
     # ---- multi-GPU: what the exchange costs, and that its result is right -------------------------------------------------
     xchg = None
     if world > 1:
-        # the same K steps without the exchange (plain graph replays): what the collective-free path does
-        for _ in range(3):
-            hp.replay()
+        # the same K pipelined steps without the exchange: what the collective-free path does
+        pipe_saved, pipe = pipe, None
+        begin()
+        for _ in range(NP):
+            step()
+        drain()
         barrier()
         ev0.record()
+        begin()
         for _ in range(args.steps):
-            hp.replay()
+            step()
+        drain()
         ev1.record()
         barrier()
+        pipe = pipe_saved
         sec_nox = ev0.elapsed_time(ev1) / 1e3
         t = torch.tensor([sec_nox], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -544,18 +580,20 @@ def main():
     st = torch.cuda.current_stream().cuda_stream
     rp = _cabi.ptrs([r.data_ptr() for r in hp._captured_inputs])
     front = os.environ.get("YL_FILTER", "split")
+    flag_name = "k_flag_raw" if os.environ.get("YL_FLAG", "tma") == "ldg" else "k_flag_tma"
 
     def flag_kernel():
         # the streaming pass alone: k_flag_raw reads every raw byte it needs once (one launch covers the three scales)
+        # (stages 1 | 4: the flag kernel alone, counters reset as in the step -- the persistent form draws its tiles from them)
         _cabi.check(L.yl_filter_raw_stage(rp, hp.fs, 3, B, C, hp.anch, hp.mask, hp.conf, hp.ws.ptr(), hp.ws.nbytes, hp.M,
-                                          hp.cap_seg, 0, B, 1, st))
+                                          hp.cap_seg, 0, B, 5, st))
 
     n_f = max(20, min(args.steps, 200))
     t_filter = time_events(torch, flag_kernel, n_f, warm=args.warmup)
     clocks = sampler.stop() if sampler else None
     peak, peak_src = measured_peaks()
     achieved = B * BYTES_PER_IMAGE / t_filter / 1e9
-    traffic = TRAFFIC_PER_LAUNCH["k_flag_raw"] if (front == "split" and B == 64) else None
+    traffic = TRAFFIC_PER_LAUNCH.get(flag_name) if (front == "split" and B == 64) else None
 
     # ---- e2e: C-ABI host-buffer call, pinned host inputs, H2D + kernels + D2H inside the timed region ------------------
     e2e = None
@@ -641,11 +679,13 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD % B,
                        "l2": "inputs (495 MB/step) are larger than L2 (126 MB); no flush needed",
-                       "timed": "CUDA-graph replay of the whole chain per step (front end %s: %s + k_segment_nms_bins + "
-                                "k_segment_nms_big + k_gather_rows)%s" % (
-                                    front, "k_flag_raw + k_emit_flagged" if front == "split" else "k_filter_raw_ws + side-stream kernels of the 19x19 scale",
-                                    "; at N>1 every step also pushes its kept rows into every rank's window (the final exchange), "
-                                    "overlapped with the next step, and the last exchange is drained inside the timed region" if world > 1 else ""),
+                       "timed": "K steps, each the CUDA-graph replay of the whole chain of one batch (%s + k_emit_flagged + k_segment_nms_bins + "
+                                "k_segment_nms_big + k_gather_rows), %d steps in flight on their own streams / workspaces / output rows; the "
+                                "timed region ends when the last step has finished%s" % (
+                                    flag_name, NP,
+                                    "; at N>1 every step also pushes its kept rows into every rank's window (the final exchange) on a side "
+                                    "stream, and the last exchange is delivered inside the timed region" if world > 1 else ""),
+                       "steps_in_flight": NP, "one_step_alone_ms": 1e3 * sec_serial / args.steps,
                        "timed_rounds": len(rounds), "round_ms_min_median_max": [1e3 * min(rounds), 1e3 * sec, 1e3 * max(rounds)],
                        "rows_per_step": rows_per_step,
                        "parallelism": "images sharded by rank, no collective inside decode/filter/NMS; final exchange by peer stores"},
@@ -654,13 +694,15 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic,
                          "frac_physical": (traffic / t_filter / 1e9 / peak) if traffic else None,
-                         "kernel": "k_flag_raw<3> (streaming decode+filter pass over the raw head tensors, one launch per step)" if front == "split"
-                                   else "front end '%s' alone (stage 1 of yl_filter_raw_stage)" % front,
+                         "kernel": "%s<3> (streaming decode+filter pass over the raw head tensors, one launch per step), timed alone" % flag_name
+                                   if front == "split" else "front end '%s' alone (stage 1 of yl_filter_raw_stage)" % front,
                          "us_per_launch": t_filter * 1e6, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": B * BYTES_PER_IMAGE,
                          "note": "frac = algorithmic bytes (all 85 planes, SURVEY 8(d)) / launch time / peak; frac_physical = the kernel's "
-                                 "own DRAM traffic (ncu capture under profiles/; it skips the 4 box planes) / the same time / peak",
-                         "whole_step_frac": (B * BYTES_PER_IMAGE / step_s / 1e9) / peak},
+                                 "own DRAM traffic (ncu capture under profiles/; it skips the 4 box planes) / the same time / peak; the peak is "
+                                 "the driver-measured COPY bandwidth (read + write), which a read-only stream can slightly exceed",
+                         "whole_step_frac": (B * BYTES_PER_IMAGE / step_s / 1e9) / peak,
+                         "whole_step_frac_one_step_alone": (B * BYTES_PER_IMAGE / (sec_serial / args.steps) / 1e9) / peak},
             "cpu_baseline": cpu,
             "parity": parity,
             "exchange": xchg,

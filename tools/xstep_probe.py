@@ -7,7 +7,8 @@ import yolov4_b200 as yb
 from yolov4_b200.synth import synth_head_outputs
 B = 64
 hps = []
-for seed in (0, 1):
+NHP = int(os.environ.get('NHP', '2'))
+for seed in range(NHP):
     raws = synth_head_outputs(B, 608, 80, seed=seed, device="cuda")
     hp = yb.HeadPostprocessor(B, [76, 38, 19], 80, 1e-4, 0.4)
     hp.ws.buf.zero_()                      # (diagnostic builds that skip a scale leave its flag words untouched)
@@ -16,8 +17,8 @@ N = 200
 def run(streams):
     for it in range(N):
         with torch.cuda.stream(streams[it % len(streams)]):
-            hps[it % 2].replay()
-for name, prios in (("serial", None), ("two streams", (0, 0)), ("two streams, prio", (0, -1))):
+            hps[it % NHP].replay()
+for name, prios in (("serial", None), ("%d streams" % NHP, (0,) * NHP)):
     streams = [torch.cuda.Stream()] if prios is None else [torch.cuda.Stream(priority=p) for p in prios]
     run(streams); torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -763,18 +763,19 @@ k_filter_raw_tma(const __grid_constant__ RawParams P, const __grid_constant__ Tm
 //                       objectness plane by a 1-D bulk copy): the bytes in flight live in shared memory, not in registers
 //                       (k_flag_raw keeps 8 CTAs x 128 threads x 64 registers busy to have 128 KB in flight per SM);
 //   * scalar warps      the scales whose planes are not 16-byte aligned (19x19: 4.8 % of the bytes), register-staged loads.
-// What it buys is not its own speed (both forms run at the HBM roofline) but ROOM: with 384 threads x <= 64 registers resident,
-// the emit / NMS CTAs of the previous image group fit next to it, so the chain's latency-bound kernels run UNDER the stream
-// instead of after it (HeadPostprocessor, n_groups > 1).
+// What it buys is not its own speed but ROOM: with 640 threads x <= 64 registers and 107 KB of shared memory resident, the emit /
+// NMS / gather CTAs of the previous steps fit next to it, so with several steps in flight (bench.py keeps three, each a CUDA graph
+// on its own stream) the chain's latency-bound kernels run UNDER the next step's stream instead of after their own:
+// 184 -> 160 us per step.  Splitting ONE step into image groups does not pay at B=64 (profiles/r2_summary.md).
 // ---------------------------------------------------------------------------------------------------------------
 #ifndef YL_FT_STREAM
 #define YL_FT_STREAM 8
 #endif
 #ifndef YL_FT_SCALAR
-#define YL_FT_SCALAR 4
+#define YL_FT_SCALAR 12                        // a scalar warp has 8 loads in flight: it takes a dozen of them per SM to hide the 19x19 scale
 #endif
 #ifndef YL_FT_STAGES
-#define YL_FT_STAGES 4
+#define YL_FT_STAGES 3
 #endif
 #ifndef YL_FT_MAXREG
 #define YL_FT_MAXREG 64
@@ -1309,10 +1310,11 @@ static const bool g_use_tma = !(getenv("YL_NO_TMA") && getenv("YL_NO_TMA")[0] ==
 // YL_FILTER selects the front-end form: "split" (default: streaming flag kernel + emit kernel) or "fused" (one kernel streams
 // and emits: the TMA pipeline where planes are 16-byte aligned, register-staged otherwise; measured slower, kept for A/B).
 static const bool g_split = !(getenv("YL_FILTER") && strcmp(getenv("YL_FILTER"), "fused") == 0);
-// YL_FLAG selects the streaming kernel of the split form: "ldg" (k_flag_raw: register-staged loads, fills the register file) or
-// "tma" (k_flag_tma: one persistent CTA per SM, TMA rings in shared memory, a quarter of the register file -- the form that
-// lets the emit / NMS CTAs of the previous image group run next to it).
-static const bool g_flag_tma = getenv("YL_FLAG") ? strcmp(getenv("YL_FLAG"), "tma") == 0 : false;
+// YL_FLAG selects the streaming kernel of the split form: "tma" (default; k_flag_tma: one persistent CTA per SM, TMA rings in shared
+// memory, 40 % of the register file and 107 KB of shared memory -- the form that lets the emit / NMS / gather CTAs of the PREVIOUS
+// steps run next to it when several steps are in flight) or "ldg" (k_flag_raw: register-staged loads, a few per cent faster alone
+// -- 81 us against 86 -- but it fills the register file, so nothing overlaps it).
+static const bool g_flag_tma = getenv("YL_FLAG") ? strcmp(getenv("YL_FLAG"), "tma") == 0 : true;
 // YL_FLAG_SMEM=<bytes, at most 48 KB>: dynamic shared memory requested (and not used) by k_flag_raw, which caps its CTAs per
 // SM so that CTAs of other kernels can be co-resident (cross-step pipelining experiments, tools/xstep_probe.py).
 static const int g_flag_smem = getenv("YL_FLAG_SMEM") ? atoi(getenv("YL_FLAG_SMEM")) : 0;
