@@ -327,7 +327,7 @@ def main():
     ap.add_argument("--min-seconds", type=float, default=0.25, help="the K-step timed region is repeated until this much device "
                                                                     "time is covered; the line reports the median round")
     ap.add_argument("--no-extras", action="store_true", help="skip the other configs' numbers")
-    ap.add_argument("--inflight", type=int, default=3, help="steps in flight: each step's chain is a CUDA graph; step i runs on stream "
+    ap.add_argument("--inflight", type=int, default=0, help="0 = automatic (3 on one GPU, 2 with the exchange at N>1).  ""steps in flight: each step's chain is a CUDA graph; step i runs on stream "
                                                             "i %% inflight with its own workspace and output rows, so the latency-bound "
                                                             "kernels of a step run under the streaming pass of the next ones (1 = serial)")
     args = ap.parse_args()
@@ -354,7 +354,7 @@ def main():
     sampler = ClockSampler(local_rank) if rank == 0 else None   # nvidia-smi needs ~0.3 s before its first sample
     raws = synth_head_outputs(B, IMG, C, seed=rank, device=dev)
     # NP postprocessors (own workspace, output rows and CUDA graph each, the same read-only inputs), one per step in flight
-    NP = max(1, min(int(args.inflight), 8))
+    NP = max(1, min(int(args.inflight), 8)) if args.inflight > 0 else (3 if world == 1 else 2)
     if world > 1:
         NP = max(NP, 2)                                  # the exchange of step i reads rows[i % NP] while step i+1 runs
     hps = [yb.HeadPostprocessor(B, GRIDS, C, CONF, NMS, device=dev, n_groups=args.groups).capture(raws) for _ in range(NP)]
@@ -373,6 +373,21 @@ def main():
         ev_pushed = [torch.cuda.Event() for _ in range(NP)]
         for e in ev_pushed:
             e.record()
+        # the exchange of a slot (push / wait / release) as a CUDA graph of its own: one host call per step instead of three kernel
+        # launches through ctypes (with three steps in flight the Python loop was the bottleneck at N>1)
+        xgraphs = []
+        for p_ in range(NP):
+            with torch.cuda.stream(side):
+                ex.push(hps[p_].rows, hps[p_].meta, p_)          # eager once on every rank: consistent epochs, warm kernels
+                ex.wait(p_)
+                ex.release(p_)
+            torch.cuda.synchronize()
+            g_ = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_, stream=side):
+                ex.push(hps[p_].rows, hps[p_].meta, p_)
+                ex.wait(p_)
+                ex.release(p_)
+            xgraphs.append(g_)
         pipe = True
 
     def barrier():
@@ -398,9 +413,7 @@ def main():
         if pipe is not None:
             side.wait_event(ev_done[p])
             with torch.cuda.stream(side):
-                ex.push(hps[p].rows, hps[p].meta, p)
-                ex.wait(p)
-                ex.release(p)
+                xgraphs[p].replay()
                 ev_pushed[p].record(side)
         state["i"] += 1
 

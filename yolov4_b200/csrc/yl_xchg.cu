@@ -160,10 +160,13 @@ __device__ __forceinline__ void mc_st1(unsigned *mc, unsigned v)
     asm volatile("multimem.st.relaxed.sys.global.u32 [%0], %1;" ::"l"(mc), "r"(v) : "memory");
 }
 
-constexpr unsigned XB_BYTES = 16384;
-constexpr int XB_STAGES = 4;
+constexpr unsigned XB_BYTES = 4096;
+constexpr int XB_STAGES = 8;
+constexpr int XB_DEPTH = 4;                    // bulk loads in flight ahead of the stores (XB_DEPTH < XB_STAGES)
 
 __device__ __forceinline__ unsigned xb_smem(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+struct XbUnit { int b; unsigned lo, len; };
 
 __global__ void __launch_bounds__(32)
 k_xchg_push_bulk(const __grid_constant__ XchgPeers P, XchgWindow mc, int rank, int world, int B, long cap_out, int slots, int slot,
@@ -190,41 +193,59 @@ k_xchg_push_bulk(const __grid_constant__ XchgPeers P, XchgWindow mc, int rank, i
         for (int s = 0; s < XB_STAGES; ++s)
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(xb_smem(&bar[s])));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        unsigned it = 0;                                               // transfers issued by this CTA: stage it % XB_STAGES
-        for (int u = blockIdx.x; u < B * n_chunks; u += gridDim.x) {
-            const int b = u / n_chunks, c = u - b * n_chunks;
-            const int n = min(max(counts[b], 0), (int)cap_out);
-            const size_t nbytes = (((size_t)n * 28 + 15) / 16) * 16;   // whole 16-byte units: the padding lies inside the image's capacity
-            const size_t lo = (size_t)c * XB_BYTES;
-            if (lo >= nbytes) continue;
-            const unsigned len = (unsigned)min((size_t)XB_BYTES, nbytes - lo);
-            const int s = (int)(it % XB_STAGES);
-            const unsigned dst_s = xb_smem(xb_stage + (size_t)s * XB_BYTES);
-            // the stage is free once the bulk stores that read it XB_STAGES transfers ago have read it: at most XB_STAGES - 1
-            // store groups may still be pending
-            asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(XB_STAGES - 1) : "memory");
-            const char *src = reinterpret_cast<const char *>(rows) + (size_t)b * img_bytes + lo;
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(xb_smem(&bar[s])), "r"(len) : "memory");
+        // The CTA's units are (image, 4 KB chunk) pairs u = blockIdx.x, + gridDim.x, ... that lie inside the image's kept rows.
+        // Two cursors walk that sequence: `up` issues the bulk loads XB_DEPTH units ahead, `uc` stores what has landed.
+        const int n_units = B * n_chunks;
+        auto next = [&](int &u, XbUnit &U) -> bool {
+            for (; u < n_units; u += gridDim.x) {
+                const int b = u / n_chunks, c = u - b * n_chunks;
+                const int n = min(max(counts[b], 0), (int)cap_out);
+                const size_t nbytes = (((size_t)n * 28 + 15) / 16) * 16;   // whole 16-byte units: the padding lies inside the image's capacity
+                const size_t lo = (size_t)c * XB_BYTES;
+                if (lo < nbytes) {
+                    U.b = b; U.lo = (unsigned)lo; U.len = (unsigned)min((size_t)XB_BYTES, nbytes - lo);
+                    u += gridDim.x;
+                    return true;
+                }
+            }
+            return false;
+        };
+        auto load = [&](const XbUnit &U, unsigned k) {
+            const int s = (int)(k % XB_STAGES);
+            // the stage is free once the store group that read it XB_STAGES units ago has read it; groups committed so far: k - XB_DEPTH
+            asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(XB_STAGES - XB_DEPTH - 1) : "memory");
+            const char *src = reinterpret_cast<const char *>(rows) + (size_t)U.b * img_bytes + U.lo;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(xb_smem(&bar[s])), "r"(U.len) : "memory");
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(dst_s), "l"(src), "r"(len), "r"(xb_smem(&bar[s])) : "memory");
+                         ::"r"(xb_smem(xb_stage + (size_t)s * XB_BYTES)), "l"(src), "r"(U.len), "r"(xb_smem(&bar[s])) : "memory");
+        };
+        int up = blockIdx.x, uc = blockIdx.x;
+        unsigned kp = 0, kc = 0;                                       // units loaded / stored
+        XbUnit U;
+        for (; kp < (unsigned)XB_DEPTH && next(up, U); ++kp) load(U, kp);
+        XbUnit V;
+        while (next(uc, V)) {
+            if (next(up, U)) { load(U, kp); ++kp; }
+            const int s = (int)(kc % XB_STAGES);
+            const unsigned parity = (kc / XB_STAGES) & 1u;
             unsigned ok;
-            const unsigned parity = (it / XB_STAGES) & 1u;
             do {
                 asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                              : "=r"(ok) : "r"(xb_smem(&bar[s])), "r"(parity) : "memory");
             } while (!ok);
-            const size_t dst_off = (((size_t)slot * world * B + (size_t)rank * B + b)) * img_bytes + lo;
+            const unsigned src_s = xb_smem(xb_stage + (size_t)s * XB_BYTES);
+            const size_t dst_off = (((size_t)slot * world * B + (size_t)rank * B + V.b)) * img_bytes + V.lo;
             if (mc.rows) {                                             // multicast mapping: one bulk store, the switch replicates
                 char *dst = reinterpret_cast<char *>(mc.rows) + dst_off;
-                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(dst_s), "r"(len) : "memory");
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_s), "r"(V.len) : "memory");
             } else {
                 for (int p = 0; p < world; ++p) {
                     char *dst = reinterpret_cast<char *>(P.w[p].rows) + dst_off;
-                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(dst_s), "r"(len) : "memory");
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_s), "r"(V.len) : "memory");
                 }
             }
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            ++it;
+            ++kc;
         }
         asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // every store of this CTA has been performed
     }
@@ -384,7 +405,10 @@ extern "C" int yl_xchg_create(yl_xchg **out, int device, int rank, int world, in
     x->limit_ns = 5000000000ull;                                     // 5 s: a missing peer is reported, not waited for forever
     x->push_ctas = getenv("YL_XCHG_CTAS") ? atoi(getenv("YL_XCHG_CTAS")) : 64;
     if (x->push_ctas < 1) x->push_ctas = 1;
-    x->bulk = !(getenv("YL_XCHG_BULK") && getenv("YL_XCHG_BULK")[0] == '0');     // YL_XCHG_BULK=0: the register-staged push
+    // YL_XCHG_BULK=1: the bulk-copy push (cp.async.bulk through shared memory).  Default: the register-staged push -- with the
+    // default TMA flag kernel holding 107 KB of every SM's shared memory the bulk form's stages get in each other's way
+    // (2 GPUs: 244 us per step against 206), and at 8 GPUs both are bound by what a rank must receive (267 vs 273 us)
+    x->bulk = getenv("YL_XCHG_BULK") && getenv("YL_XCHG_BULK")[0] == '1';
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaMalloc(&x->window, x->L.total);
     // flags, acks, epochs, counters start at zero; the row area needs no initialisation
@@ -415,11 +439,10 @@ extern "C" int yl_xchg_create_external(yl_xchg **out, int device, int rank, int 
     x->device = device; x->rank = rank; x->world = world; x->B = B; x->cap_out = cap_out; x->slots = slots;
     x->L = xchg_layout(world, B, cap_out, slots);
     x->limit_ns = 5000000000ull;
-    // through the multicast mapping a rank sends 1/world of the bytes: 16 single-warp CTAs keep the switch busy (8 GPUs: 267 us per
-    // step with 16, 273 us with 64), the peer-store forms want 64
-    x->push_ctas = getenv("YL_XCHG_CTAS") ? atoi(getenv("YL_XCHG_CTAS")) : (multicast ? 16 : 64);
+    // through the multicast mapping a rank sends 1/world of the bytes: 32 CTAs are enough, the peer-store forms want 64
+    x->push_ctas = getenv("YL_XCHG_CTAS") ? atoi(getenv("YL_XCHG_CTAS")) : (multicast ? 32 : 64);
     if (x->push_ctas < 1) x->push_ctas = 1;
-    x->bulk = !(getenv("YL_XCHG_BULK") && getenv("YL_XCHG_BULK")[0] == '0');
+    x->bulk = getenv("YL_XCHG_BULK") && getenv("YL_XCHG_BULK")[0] == '1';
     x->external = true;
     for (int p = 0; p < world; ++p) { x->peer[p] = (char *)windows[p]; x->P.w[p] = window_of(x->peer[p], x->L); }
     x->window = x->peer[rank];
