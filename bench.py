@@ -339,6 +339,11 @@ def main():
         run_reference(args, rank, world)
         return
     args.warmup = max(args.warmup, 3)
+    if world > 1:
+        # With the exchange in the step the register-staged flag kernel measured best (it uses no shared memory, the bulk-copy push
+        # of the exchange lives in it): 8 GPUs 268 us per step against 300-356 us with the TMA flag kernel (profiles/r2_summary.md).
+        # Read once when the library loads, so set before anything touches it.
+        os.environ.setdefault("YL_FLAG", "ldg")
 
     import torch
     import torch.distributed as dist

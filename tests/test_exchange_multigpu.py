@@ -106,8 +106,8 @@ def test_exchange_single_rank_self_window():
     _run(1)
 
 
-def test_exchange_single_rank_bulk_copy_push(monkeypatch):
-    monkeypatch.setenv("YL_XCHG_BULK", "1")          # read by yl_xchg_create in the spawned worker
+def test_exchange_single_rank_register_staged_push(monkeypatch):
+    monkeypatch.setenv("YL_XCHG_BULK", "0")          # read by yl_xchg_create in the spawned worker
     _run(1)
 
 

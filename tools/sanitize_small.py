@@ -45,7 +45,7 @@ rows, meta = hp.run(raws)
 out = yb.coco_rows_padded(rows, meta[:2], [[480, 640, 312, 416]] * 2, [7, 9], list(range(1, 81)))
 ok &= out.shape[0] == int(meta[:2].sum())
 from yolov4_b200.sharded import DetectionExchange
-for bulk in ("0", "1"):
+for bulk in ("1", "0"):
     os.environ["YL_XCHG_BULK"] = bulk
     ex = DetectionExchange(2, 8192, torch.device("cuda", 0), slots=2)
     for slot in (0, 1, 0):

@@ -160,9 +160,10 @@ __device__ __forceinline__ void mc_st1(unsigned *mc, unsigned v)
     asm volatile("multimem.st.relaxed.sys.global.u32 [%0], %1;" ::"l"(mc), "r"(v) : "memory");
 }
 
-constexpr unsigned XB_BYTES = 4096;
-constexpr int XB_STAGES = 8;
-constexpr int XB_DEPTH = 4;                    // bulk loads in flight ahead of the stores (XB_DEPTH < XB_STAGES)
+constexpr unsigned XB_BYTES = 16384;
+constexpr int XB_STAGES = 4;
+constexpr int XB_DEPTH = 1;                    // bulk loads in flight ahead of the stores (XB_DEPTH < XB_STAGES); deeper look-ahead with
+                                               // 4 KB units measured no better (the push is not what bounds the exchange)
 
 __device__ __forceinline__ unsigned xb_smem(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
@@ -405,10 +406,7 @@ extern "C" int yl_xchg_create(yl_xchg **out, int device, int rank, int world, in
     x->limit_ns = 5000000000ull;                                     // 5 s: a missing peer is reported, not waited for forever
     x->push_ctas = getenv("YL_XCHG_CTAS") ? atoi(getenv("YL_XCHG_CTAS")) : 64;
     if (x->push_ctas < 1) x->push_ctas = 1;
-    // YL_XCHG_BULK=1: the bulk-copy push (cp.async.bulk through shared memory).  Default: the register-staged push -- with the
-    // default TMA flag kernel holding 107 KB of every SM's shared memory the bulk form's stages get in each other's way
-    // (2 GPUs: 244 us per step against 206), and at 8 GPUs both are bound by what a rank must receive (267 vs 273 us)
-    x->bulk = getenv("YL_XCHG_BULK") && getenv("YL_XCHG_BULK")[0] == '1';
+    x->bulk = !(getenv("YL_XCHG_BULK") && getenv("YL_XCHG_BULK")[0] == '0');     // YL_XCHG_BULK=0: the register-staged push
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaMalloc(&x->window, x->L.total);
     // flags, acks, epochs, counters start at zero; the row area needs no initialisation
@@ -439,10 +437,11 @@ extern "C" int yl_xchg_create_external(yl_xchg **out, int device, int rank, int 
     x->device = device; x->rank = rank; x->world = world; x->B = B; x->cap_out = cap_out; x->slots = slots;
     x->L = xchg_layout(world, B, cap_out, slots);
     x->limit_ns = 5000000000ull;
-    // through the multicast mapping a rank sends 1/world of the bytes: 32 CTAs are enough, the peer-store forms want 64
-    x->push_ctas = getenv("YL_XCHG_CTAS") ? atoi(getenv("YL_XCHG_CTAS")) : (multicast ? 32 : 64);
+    // through the multicast mapping a rank sends 1/world of the bytes: 16 single-warp CTAs keep the switch busy (8 GPUs: 267 us per
+    // step with 16, 273 us with 64), the peer-store forms want 64
+    x->push_ctas = getenv("YL_XCHG_CTAS") ? atoi(getenv("YL_XCHG_CTAS")) : (multicast ? 16 : 64);
     if (x->push_ctas < 1) x->push_ctas = 1;
-    x->bulk = getenv("YL_XCHG_BULK") && getenv("YL_XCHG_BULK")[0] == '1';
+    x->bulk = !(getenv("YL_XCHG_BULK") && getenv("YL_XCHG_BULK")[0] == '0');
     x->external = true;
     for (int p = 0; p < world; ++p) { x->peer[p] = (char *)windows[p]; x->P.w[p] = window_of(x->peer[p], x->L); }
     x->window = x->peer[rank];
