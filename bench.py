@@ -363,7 +363,13 @@ def main():
     if world > 1:
         NP = max(NP, 2)                                  # the exchange of step i reads rows[i % NP] while step i+1 runs
     hps = [yb.HeadPostprocessor(B, GRIDS, C, CONF, NMS, device=dev, n_groups=args.groups).capture(raws) for _ in range(NP)]
-    cstreams = [torch.cuda.Stream(device=dev) for _ in range(NP)]
+    if world == 1:
+        cstreams = [torch.cuda.Stream(device=dev) for _ in range(NP)]
+    else:
+        # with the exchange in the step the chains run one after the other on ONE stream (two output buffers alternate, the
+        # exchange of step i runs under the chain of step i+1 on the side stream): concurrent chains measured slower there
+        # (8 GPUs: 342 us per step against 268)
+        cstreams = [torch.cuda.Stream(device=dev)] * NP
     hp = hps[0]
     res = hp.results()                                   # validates capacities; also the first parity-visible output
     rows_per_step = sum(0 if r is None else r.shape[0] for r in res)
@@ -378,10 +384,10 @@ def main():
         ev_pushed = [torch.cuda.Event() for _ in range(NP)]
         for e in ev_pushed:
             e.record()
-        # the exchange of a slot (push / wait / release) as a CUDA graph of its own: one host call per step instead of three kernel
-        # launches through ctypes (with three steps in flight the Python loop was the bottleneck at N>1)
+        # (YL_BENCH_XGRAPH=1: the exchange of a slot -- push / wait / release -- as a CUDA graph of its own, one host call per step
+        # instead of three kernel launches through ctypes; measured no faster, the eager launches are the default)
         xgraphs = []
-        for p_ in range(NP):
+        for p_ in range(NP if os.environ.get("YL_BENCH_XGRAPH") == "1" else 0):
             with torch.cuda.stream(side):
                 ex.push(hps[p_].rows, hps[p_].meta, p_)          # eager once on every rank: consistent epochs, warm kernels
                 ex.wait(p_)
@@ -418,7 +424,12 @@ def main():
         if pipe is not None:
             side.wait_event(ev_done[p])
             with torch.cuda.stream(side):
-                xgraphs[p].replay()
+                if xgraphs:
+                    xgraphs[p].replay()
+                else:
+                    ex.push(hps[p].rows, hps[p].meta, p)
+                    ex.wait(p)
+                    ex.release(p)
                 ev_pushed[p].record(side)
         state["i"] += 1
 
